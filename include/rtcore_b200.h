@@ -1,0 +1,238 @@
+/*
+ * rtcore_b200.h — C ABI of librtcore_b200.so, the B200 (sm_100a) wavefront path-tracing backend that
+ * replaces the CPU render loop of Zaggy1024/RaytracerCore.
+ *
+ * The reference has no FFI of its own; the seam this ABI replaces is the managed call chain
+ *   FullRaytracer.Start -> Raytracer.Render -> Raytracer.GetColor -> Scene.RayTrace -> SampleSet
+ * (RaytracerCore/Raytracing/FullRaytracer.cs:243, Raytracer.cs:294/:65, Scene.cs:113, SampleSet.cs:32).
+ * Each entry point below names the reference member it stands in for. All pointers are plain host
+ * pointers unless a name says "device"; arrays are caller-owned and copied during the call. One host
+ * thread per handle at a time, one handle per GPU. Every function returns RTC_OK (0) or an RTC_ERR_* code;
+ * rtc_last_error() gives the text. There is no CPU fallback: without a CUDA device rtc_create() fails.
+ */
+#ifndef RTCORE_B200_H
+#define RTCORE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTC_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------------------------- */
+enum {
+  RTC_OK = 0,
+  RTC_ERR_INVALID = 1,   /* bad argument (null pointer, negative count, index out of range)            */
+  RTC_ERR_CUDA = 2,      /* a CUDA runtime call failed; text in rtc_last_error                         */
+  RTC_ERR_STATE = 3,     /* call order violated (e.g. render before scene/bvh/camera/params are set)   */
+  RTC_ERR_NOMEM = 4,     /* host or device allocation failed                                           */
+  RTC_ERR_UNSUPPORTED = 5,
+  RTC_ERR_NCCL = 6
+};
+
+/* ---- arithmetic mode ------------------------------------------------------------------------------- */
+enum {
+  RTC_F32 = 0,           /* production mode: float geometry/BVH, tolerance 1e-4 against the f64 oracle  */
+  RTC_F64 = 1            /* parity mode: restates the reference's IEEE-f64 arithmetic operation by      */
+                         /* operation (FMA exactly where the reference's AVX path fuses)                */
+};
+
+/* ---- primitives: Raytracing/Primitives/{Primitive,Triangle,Sphere,Plane}.cs ------------------------- */
+enum {
+  RTC_KIND_TRIANGLE = 0, /* Triangle.cs — also the parallelogram ("Mirror") used by every Cube face      */
+  RTC_KIND_SPHERE = 1,   /* Sphere.cs — optionally affine-transformed (RTC_FLAG_TRANSFORMED)            */
+  RTC_KIND_PLANE = 2     /* Plane.cs                                                                    */
+};
+
+enum {
+  RTC_FLAG_MIRROR = 1,       /* Triangle.Mirror        (Triangle.cs:25)                                 */
+  RTC_FLAG_TWOSIDED = 2,     /* Primitive.TwoSided     (Primitive.cs:88)                                */
+  RTC_FLAG_INVERT = 4,       /* Primitive.Invert       (Primitive.cs:92)                                */
+  RTC_FLAG_TRANSFORMED = 8,  /* Sphere.Transformed     (Sphere.cs:16)                                   */
+  RTC_FLAG_VNORMALS = 16     /* Triangle.HasNormals    (Triangle.cs:26); vnormals[] row is used         */
+};
+
+#define RTC_GEOM_STRIDE 12
+#define RTC_MATERIAL_STRIDE 14
+#define RTC_XFORM_STRIDE 48
+
+/*
+ * Flattened Scene.Primitives (Scene.cs:160), indexed by Primitive.ID (= insertion order, Scene.cs:58-63).
+ *   geom[i*12..]   triangle: Vert0.Position xyz, Edge0to1 xyz, Edge0to2 xyz, Normal xyz (Triangle.cs:22-29,54-66)
+ *                  sphere:   Center xyz, RadiusValue, RadiusSqr, 7 unused              (Sphere.cs:11-14)
+ *                  plane:    Normal xyz, OriginDistance, 8 unused                      (Plane.cs:13-14)
+ *   xform[i]       row in xforms[] for a transformed sphere / vertex-normal triangle, else -1
+ *   xforms[j*48..] sphere:   MatrixToWorld (=world->object), MatrixToObject (=object->world), MatrixToNormal,
+ *                            each 16 doubles row-major D00..D33 (Sphere.cs:17-19, Mat4x4D.cs:21-39)
+ *                  triangle: Vert0.Normal, Vert1.Normal, Vert2.Normal (9 doubles), rest unused
+ *   material[i*14..] Emission rgb, Diffuse rgb, Specular rgb, Refraction rgb (raw backing fields),
+ *                  RefractiveIndex, Shininess                                          (Primitive.cs:16-129)
+ */
+typedef struct rtc_scene_desc {
+  int32_t n_prims;
+  int32_t n_xforms;
+  const uint8_t* kind;
+  const uint8_t* flags;
+  const double* geom;
+  const int32_t* xform;    /* may be NULL when n_xforms == 0 */
+  const double* xforms;    /* may be NULL when n_xforms == 0 */
+  const double* material;
+} rtc_scene_desc;
+
+/*
+ * One node of the reference-shaped binary BVH (Acceleration/BVH.cs:239-285): Volume (AABB.Minimum/Maximum,
+ * AABB.cs:45-46), Left/Right as node indices, and for leaves (IsLeaf) the LeafID = primitive ID. Exactly one
+ * primitive per leaf (BVH.cs:256-264). Infinite boxes (planes, Plane.cs:68-74) are allowed.
+ */
+typedef struct rtc_bvh_node {
+  double bmin[3];
+  double bmax[3];
+  int32_t left;   /* node index, -1 for a leaf */
+  int32_t right;  /* node index, -1 for a leaf */
+  int32_t prim;   /* primitive ID for a leaf, -1 for an inner node */
+  int32_t pad;
+} rtc_bvh_node;
+
+/* Camera after Camera.InitRender / FrustumCamera.InitRender / OrthoCamera.InitRender
+ * (Cameras/Camera.cs:54-63, FrustumCamera.cs:24-31, OrthoCamera.cs:22-31). */
+enum { RTC_CAMERA_FRUSTUM = 0, RTC_CAMERA_ORTHO = 1 };
+typedef struct rtc_camera {
+  int32_t kind;
+  int32_t pad;
+  double position[3];
+  double look[3];
+  double side[3];
+  double up[3];
+  double w2, h2;
+  double tan_fov_x2, tan_fov_y2; /* frustum: tanFOVX2, tanFOVY2 (already negated, FrustumCamera.cs:30) */
+  double h_mult, v_mult;         /* ortho: hMult, vMult (OrthoCamera.cs:29-30)                         */
+  double image_plane, dof_amount, focal_length; /* Camera.cs:25-27 */
+} rtc_camera;
+
+/* Scene globals read by the render loop (Scene.cs:16-35). ambient == (-1,-1,-1) is DoubleColor.Placeholder,
+ * i.e. "ambient miss" (SceneLoader.cs:183-188): bounced misses then count as Misses. */
+typedef struct rtc_params {
+  int32_t width, height;
+  int32_t recursion;
+  int32_t debug_geom;
+  double ambient[3];
+  double air_ior;       /* Scene.AirRefractiveIndex, 1.000293 */
+  uint64_t seed;        /* Philox4x32-10 key; replaces the unseeded System.Random of Raytracer.cs:48 */
+} rtc_params;
+
+/* Ray (Vectors/Ray.cs:27-29) and Hit (Raytracing/Hit.cs:14-20). prim == -1 means "no hit" / "no skip". */
+typedef struct rtc_ray {
+  double origin[3];
+  double dir[3];
+} rtc_ray;
+
+typedef struct rtc_hit {
+  int32_t prim;
+  int32_t inside;
+  double t;            /* Hit.Distance */
+  double position[3];
+  double normal[3];
+} rtc_hit;
+
+/* Per-bounce record of Raytracer.DebugRay (Raytracer.cs:28-33); type uses Raytracer.BounceType order (:14-26). */
+typedef struct rtc_debug_ray {
+  rtc_hit hit;
+  int32_t type;
+  int32_t pad;
+  double fresnel_ratio;
+} rtc_debug_ray;
+
+enum {
+  RTC_K_RAYGEN = 0, RTC_K_TRACE = 1, RTC_K_SHADE = 2, RTC_K_COMPACT = 3, RTC_K_ACCUMULATE = 4, RTC_K_COUNT = 5
+};
+
+typedef struct rtc_stats {
+  uint64_t paths;                 /* camera paths started (== Raytracer.GetColor(x,y) calls)            */
+  uint64_t rays;                  /* closest-hit queries (== Scene.RayTrace calls), all bounces          */
+  uint64_t launches[RTC_K_COUNT]; /* kernel launches per kernel family                                   */
+  double ms[RTC_K_COUNT];         /* CUDA-event time per kernel family (only while timing is enabled)    */
+  uint64_t nodes_visited;         /* only with rtc_set_option(RTC_OPT_COUNTERS,1): BVH nodes fetched     */
+  uint64_t prims_tested;          /*   "                                          primitive tests        */
+} rtc_stats;
+
+enum {
+  RTC_OPT_KERNEL_TIMING = 1, /* record CUDA events around every launch (rtc_stats.ms)                  */
+  RTC_OPT_COUNTERS = 2,      /* instrumented traversal (nodes_visited / prims_tested)                  */
+  RTC_OPT_MAX_PATHS = 3,     /* size of the path pool (paths in flight per wavefront)                   */
+  RTC_OPT_SORT_RAYS = 4      /* reserved                                                                */
+};
+
+/* ---- lifetime -------------------------------------------------------------------------------------- */
+typedef struct rtc_ctx rtc_ctx;
+
+int rtc_abi_version(void);
+/* Number of CUDA devices visible (0 when there is none or the driver is missing). */
+int rtc_device_count(void);
+/* FullRaytracer ctor (FullRaytracer.cs:66): one context per GPU. precision is RTC_F32 or RTC_F64. */
+int rtc_create(int device, int precision, rtc_ctx** out);
+void rtc_destroy(rtc_ctx* ctx);
+/* Text of the last error on this context (ctx == NULL: last error of a failed rtc_create on this thread). */
+const char* rtc_last_error(rtc_ctx* ctx);
+int rtc_set_option(rtc_ctx* ctx, int option, int64_t value);
+
+/* ---- scene hand-over: what Scene.Prepare + FullRaytracer.Start set up (FullRaytracer.cs:253-269) ----- */
+/* Scene.Primitives + materials (Scene.cs:28,160). Invalidates any BVH previously set. */
+int rtc_upload_scene(rtc_ctx* ctx, const rtc_scene_desc* scene);
+/* Scene.Accelerator as built by the host (BVH.Construct, BVH.cs:193): reference topology, n_nodes nodes. */
+int rtc_upload_bvh(rtc_ctx* ctx, int32_t n_nodes, const rtc_bvh_node* nodes, int32_t root);
+/* Replacement for BVH.Construct (BVH.cs:50-236): binned-SAH build over the uploaded primitives, leaf boxes
+ * exactly as AABB.CreateFromBounded (AABB.cs:20-36); planes are chained above the root. */
+int rtc_build_bvh(rtc_ctx* ctx);
+/* Read the current tree back in reference shape (for SceneInspector.cs:226-265 and for the parity oracle). */
+int rtc_get_bvh_size(rtc_ctx* ctx, int32_t* n_nodes, int32_t* root);
+int rtc_get_bvh(rtc_ctx* ctx, int32_t capacity, rtc_bvh_node* nodes);
+/* Scene.Camera after InitRender (FullRaytracer.cs:269). */
+int rtc_set_camera(rtc_ctx* ctx, const rtc_camera* camera);
+/* Scene.Width/Height/Recursion/AmbientRGB/DebugGeom/AirRefractiveIndex. Changing width/height reallocates
+ * and clears the accumulation buffer (new SampleSet[w,h], FullRaytracer.cs:259-266). */
+int rtc_set_params(rtc_ctx* ctx, const rtc_params* params);
+
+/* ---- the hot path ---------------------------------------------------------------------------------- */
+/* Scene.RayTrace(ray, skipHit) (Scene.cs:113-120) for n rays. skip may be NULL (== default(Hit) for all). */
+int rtc_trace_closest(rtc_ctx* ctx, int64_t n, const rtc_ray* rays, const rtc_hit* skip, rtc_hit* out);
+/* Raytracer.GetCameraRay (Raytracer.cs:262-282) for n (x, y, sample) triples; xy is n*2 int32. */
+int rtc_camera_rays(rtc_ctx* ctx, int64_t n, const int32_t* xy, const uint32_t* sample, rtc_ray* out);
+/* n_samples passes of Raytracer.Render over the pixel rectangle [x0,x1) x [y0,y1) (Raytracer.cs:302-327),
+ * samples first_sample .. first_sample+n_samples-1 of every pixel, accumulated like FullRaytracer.cs:326-339.
+ * Asynchronous on the context's stream; rtc_sync / rtc_read_accum / rtc_tonemap_argb wait for it. */
+int rtc_render(rtc_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1, uint32_t first_sample, uint32_t n_samples);
+int rtc_sync(rtc_ctx* ctx);
+
+/* ---- SampleSet[,] (SampleSet.cs:7-44): row-major y*width+x ------------------------------------------ */
+int rtc_clear_accum(rtc_ctx* ctx);
+int rtc_read_accum(rtc_ctx* ctx, double* rgb_sum, uint32_t* samples, uint32_t* misses);
+int rtc_write_accum(rtc_ctx* ctx, const double* rgb_sum, const uint32_t* samples, const uint32_t* misses);
+/* Device addresses of the accumulation planes (rgb_sum: w*h*3 f64, samples / misses: w*h u32), for the
+ * per-frame collective. */
+int rtc_accum_device_ptrs(rtc_ctx* ctx, void** rgb_sum, void** samples, void** misses);
+/* FullRaytracer.GetBitmap / SampleSet.GetOutput (FullRaytracer.cs:179-205, SampleSet.cs:61-113): ARGB8. */
+int rtc_tonemap_argb(rtc_ctx* ctx, double exposure, const double back_rgb[3], double back_a, uint32_t* argb);
+
+/* ---- inspection ------------------------------------------------------------------------------------ */
+/* Raytracer.GetDebugTrace(x, y) (Raytracer.cs:254-260,289-292) for one (pixel, sample); *n <= recursion+1. */
+int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t capacity, rtc_debug_ray* out, int32_t* n);
+/* Per-path radiance of one sample pass (== the DoubleColor[w,h] a tile hands to OnTileFinished,
+ * Raytracer.cs:305-326), rgb = (-1,-1,-1) for misses. out is w*h*3 doubles over the full image. */
+int rtc_render_samples(rtc_ctx* ctx, uint32_t sample, double* out_rgb);
+int rtc_get_stats(rtc_ctx* ctx, rtc_stats* stats);
+int rtc_reset_stats(rtc_ctx* ctx);
+
+/* ---- multi-GPU: scene replicated, sample ranges per rank, one collective per frame ------------------ */
+#define RTC_NCCL_ID_BYTES 128
+int rtc_comm_unique_id(void* id128);
+int rtc_comm_init(rtc_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
+/* Sum rgb_sum / samples / misses of all ranks into `root` (ncclReduce over NVLink), root < 0: all-reduce. */
+int rtc_reduce_accum(rtc_ctx* ctx, int32_t root);
+int rtc_comm_destroy(rtc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1132 @@
+// rtc_api.cu — the C ABI of include/rtcore_b200.h: context, scene hand-over (host f64 arrays -> device SoA +
+// flattened BVH), the wavefront loop that sequences the kernels, accumulation-buffer I/O, stats and the
+// per-frame NCCL collective. Kernels live in kernels_f32.cu / kernels_f64.cu (rtc_device.cuh).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../host/scene.h"
+#include "rtc_internal.h"
+
+using namespace rtc;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct NcclId {
+  char internal[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) {
+      err = std::string("cannot load libnccl: ") + dlerror();
+      return false;
+    }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    Reduce = (decltype(Reduce))dlsym(lib, "ncclReduce");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !Reduce || !AllReduce || !GroupStart || !GroupEnd) {
+      err = "libnccl is missing required symbols";
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclUint32 = 3, kNcclSum = 0;
+
+struct TimedLaunch {
+  cudaEvent_t a, b;
+  int kind;
+};
+}  // namespace
+
+struct rtc_ctx {
+  int device = 0;
+  int precision = RTC_F32;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+
+  // host copy of the scene as handed over (f64)
+  int32_t n_prims = 0, n_xforms = 0;
+  std::vector<uint8_t> kind, flags;
+  std::vector<double> geom, xforms, material;
+  std::vector<int32_t> xform;
+  std::vector<rtc_bvh_node> nodes;
+  int32_t root = -1;
+  bool scene_set = false, bvh_set = false, camera_set = false, params_set = false;
+  rtc_camera cam{};
+  rtc_params par{};
+
+  // device scene
+  void *d_nodes = nullptr, *d_prims = nullptr, *d_xforms = nullptr, *d_mats = nullptr;
+  int32_t *d_aux = nullptr, *d_prim_id = nullptr, *d_id_to_slot = nullptr;
+  uint32_t* d_prim_ref = nullptr;
+  uint32_t root_node = 0;
+  int bvh_depth = 0;
+
+  // path pool
+  int64_t max_paths = 1 << 23;
+  int64_t pool_cap = 0;
+  void *d_dir = nullptr, *d_tint = nullptr, *d_hpos[2] = {nullptr, nullptr}, *d_hnrm[2] = {nullptr, nullptr},
+       *d_radiance = nullptr, *d_skip_pos = nullptr;
+  uint32_t* d_queue[2] = {nullptr, nullptr};
+  Control* d_ctl = nullptr;
+  int32_t* d_dbg_type = nullptr;
+  void* d_dbg_fresnel = nullptr;
+  // rtc_trace_closest staging
+  rtc_ray* d_rays = nullptr;
+  rtc_hit *d_skip = nullptr, *d_hits = nullptr;
+  int64_t stage_cap = 0;
+
+  // accumulation planes (SampleSet[,])
+  double* d_rgb = nullptr;
+  uint32_t *d_samples = nullptr, *d_misses = nullptr;
+  int acc_w = 0, acc_h = 0;
+
+  // stats
+  rtc_stats stats{};
+  bool timing = false, counters = false;
+  std::vector<TimedLaunch> pending;
+  std::vector<cudaEvent_t> free_events;
+
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+namespace {
+
+int fail(rtc_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(ctx, RTC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
+  } while (0)
+
+size_t rsize(const rtc_ctx* c) { return c->precision == RTC_F64 ? sizeof(double) : sizeof(float); }
+
+void free_dev(void*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+template <typename T>
+void free_dev_t(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void free_scene_device(rtc_ctx* c) {
+  free_dev(c->d_nodes);
+  free_dev(c->d_prims);
+  free_dev(c->d_xforms);
+  free_dev(c->d_mats);
+  free_dev_t(c->d_aux);
+  free_dev_t(c->d_prim_id);
+  free_dev_t(c->d_id_to_slot);
+  free_dev_t(c->d_prim_ref);
+}
+
+void free_pool(rtc_ctx* c) {
+  free_dev(c->d_dir);
+  free_dev(c->d_tint);
+  for (int i = 0; i < 2; i++) {
+    free_dev(c->d_hpos[i]);
+    free_dev(c->d_hnrm[i]);
+    free_dev_t(c->d_queue[i]);
+  }
+  free_dev(c->d_radiance);
+  free_dev(c->d_skip_pos);
+  free_dev_t(c->d_dbg_type);
+  free_dev(c->d_dbg_fresnel);
+  c->pool_cap = 0;
+}
+
+int ensure_pool(rtc_ctx* ctx, int64_t want) {
+  if (ctx->pool_cap >= want && ctx->d_dir) return RTC_OK;
+  free_pool(ctx);
+  size_t v4 = rsize(ctx) * 4;
+  CU(cudaMalloc(&ctx->d_dir, v4 * want));
+  CU(cudaMalloc(&ctx->d_tint, v4 * want));
+  for (int i = 0; i < 2; i++) {
+    CU(cudaMalloc(&ctx->d_hpos[i], v4 * want));
+    CU(cudaMalloc(&ctx->d_hnrm[i], v4 * want));
+    CU(cudaMalloc((void**)&ctx->d_queue[i], sizeof(uint32_t) * want));
+  }
+  CU(cudaMalloc(&ctx->d_radiance, v4 * want));
+  if (!ctx->d_ctl) {
+    CU(cudaMalloc((void**)&ctx->d_ctl, sizeof(Control)));
+    CU(cudaMemset(ctx->d_ctl, 0, sizeof(Control)));
+  }
+  ctx->pool_cap = want;
+  return RTC_OK;
+}
+
+template <typename R>
+PathView<R> path_view(rtc_ctx* c) {
+  PathView<R> pv;
+  pv.dir = (V4<R>*)c->d_dir;
+  pv.tint = (V4<R>*)c->d_tint;
+  for (int i = 0; i < 2; i++) {
+    pv.hpos[i] = (V4<R>*)c->d_hpos[i];
+    pv.hnrm[i] = (V4<R>*)c->d_hnrm[i];
+    pv.queue[i] = c->d_queue[i];
+  }
+  pv.radiance = (V4<R>*)c->d_radiance;
+  pv.skip_pos = nullptr;
+  pv.ctl = c->d_ctl;
+  pv.dbg_type = nullptr;
+  pv.dbg_fresnel = nullptr;
+  return pv;
+}
+
+template <typename R>
+SceneView<R> scene_view(rtc_ctx* c) {
+  SceneView<R> sv;
+  sv.nodes = (const DNode<R>*)c->d_nodes;
+  sv.prims = (const DPrim<R>*)c->d_prims;
+  sv.xforms = (const DXform<R>*)c->d_xforms;
+  sv.mats = (const DMat<R>*)c->d_mats;
+  sv.aux = c->d_aux;
+  sv.prim_id = c->d_prim_id;
+  sv.prim_ref = c->d_prim_ref;
+  sv.root = c->root_node;
+  sv.n_prims = c->n_prims;
+  return sv;
+}
+
+template <typename R>
+CameraView<R> camera_view(const rtc_camera& c) {
+  CameraView<R> v;
+  v.kind = c.kind;
+  for (int i = 0; i < 3; i++) {
+    v.position[i] = (R)c.position[i];
+    v.look[i] = (R)c.look[i];
+    v.side[i] = (R)c.side[i];
+    v.up[i] = (R)c.up[i];
+  }
+  v.w2 = (R)c.w2;
+  v.h2 = (R)c.h2;
+  v.tan_fov_x2 = (R)c.tan_fov_x2;
+  v.tan_fov_y2 = (R)c.tan_fov_y2;
+  v.h_mult = (R)c.h_mult;
+  v.v_mult = (R)c.v_mult;
+  v.image_plane = (R)c.image_plane;
+  v.dof_amount = (R)c.dof_amount;
+  v.focal_length = (R)c.focal_length;
+  return v;
+}
+
+template <typename R>
+ParamsView<R> params_view(const rtc_params& p) {
+  ParamsView<R> v;
+  v.width = p.width;
+  v.height = p.height;
+  v.recursion = p.recursion;
+  v.debug_geom = p.debug_geom;
+  for (int i = 0; i < 3; i++) v.ambient[i] = (R)p.ambient[i];
+  v.air_ior = (R)p.air_ior;
+  v.seed_lo = (uint32_t)p.seed;
+  v.seed_hi = (uint32_t)(p.seed >> 32);
+  return v;
+}
+
+// f64 -> R with outward rounding for box bounds
+template <typename R>
+R round_down(double x) {
+  if constexpr (std::is_same<R, double>::value) return x;
+  else {
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+    return f;
+  }
+}
+template <typename R>
+R round_up(double x) {
+  if constexpr (std::is_same<R, double>::value) return x;
+  else {
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+    return f;
+  }
+}
+
+// Flatten the reference-shaped tree + primitives into the device layout (see rtc_internal.h).
+template <typename R>
+int build_device_scene(rtc_ctx* ctx) {
+  const int32_t n = ctx->n_prims;
+  const int32_t nn = (int32_t)ctx->nodes.size();
+  const std::vector<rtc_bvh_node>& nodes = ctx->nodes;
+  if (ctx->root < 0 || ctx->root >= nn) return fail(ctx, RTC_ERR_INVALID, "BVH root out of range");
+  if (n > (int32_t)REF_SLOT_MASK) return fail(ctx, RTC_ERR_UNSUPPORTED, "more than 2^26-1 primitives");
+
+  std::vector<int32_t> inner_idx(nn, -1), leaf_slot(nn, -1);
+  std::vector<int32_t> slot_prim;
+  slot_prim.reserve(n);
+  std::vector<uint8_t> prim_seen(n, 0);
+  struct It {
+    int32_t node, depth;
+  };
+  std::vector<It> st;
+  st.push_back({ctx->root, 0});
+  int32_t n_inner = 0, visited = 0, max_depth = 0;
+  while (!st.empty()) {
+    It it = st.back();
+    st.pop_back();
+    if (++visited > nn) return fail(ctx, RTC_ERR_INVALID, "BVH is not a tree (node reached twice)");
+    const rtc_bvh_node& nd = nodes[it.node];
+    max_depth = std::max(max_depth, it.depth);
+    if (nd.prim >= 0) {
+      if (nd.prim >= n) return fail(ctx, RTC_ERR_INVALID, "BVH leaf references a primitive out of range");
+      if (prim_seen[nd.prim]) return fail(ctx, RTC_ERR_INVALID, "primitive referenced by two BVH leaves");
+      prim_seen[nd.prim] = 1;
+      leaf_slot[it.node] = (int32_t)slot_prim.size();
+      slot_prim.push_back(nd.prim);
+    } else {
+      if (nd.left < 0 || nd.left >= nn || nd.right < 0 || nd.right >= nn)
+        return fail(ctx, RTC_ERR_INVALID, "BVH child index out of range");
+      if (inner_idx[it.node] >= 0) return fail(ctx, RTC_ERR_INVALID, "BVH is not a tree (node reached twice)");
+      inner_idx[it.node] = n_inner++;
+      st.push_back({nd.right, it.depth + 1});
+      st.push_back({nd.left, it.depth + 1});  // left is processed first: left-first leaf order (BVH.cs:314-315)
+    }
+  }
+  if ((int32_t)slot_prim.size() != n) return fail(ctx, RTC_ERR_INVALID, "BVH does not reference every primitive exactly once");
+  if (max_depth > kTraceStack) return fail(ctx, RTC_ERR_UNSUPPORTED, "BVH depth " + std::to_string(max_depth) + " exceeds the traversal stack (" + std::to_string(kTraceStack) + ")");
+  ctx->bvh_depth = max_depth;
+
+  auto leaf_ref = [&](int32_t node) -> uint32_t {
+    int32_t p = nodes[node].prim;
+    uint8_t k = ctx->kind[p], f = ctx->flags[p];
+    uint32_t dk = k == RTC_KIND_TRIANGLE ? DK_TRI : k == RTC_KIND_PLANE ? DK_PLANE : ((f & RTC_FLAG_TRANSFORMED) && ctx->xform[p] >= 0) ? DK_XSPHERE : DK_SPHERE;
+    uint32_t r = REF_LEAF | (dk << REF_KIND_SHIFT) | (uint32_t)leaf_slot[node];
+    if (f & RTC_FLAG_MIRROR) r |= REF_MIRROR;
+    if (f & RTC_FLAG_TWOSIDED) r |= REF_TWOSIDED;
+    if (f & RTC_FLAG_INVERT) r |= REF_INVERT;
+    return r;
+  };
+  auto child_ref = [&](int32_t node) -> uint32_t { return nodes[node].prim >= 0 ? leaf_ref(node) : (uint32_t)inner_idx[node]; };
+
+  const bool single_leaf = nodes[ctx->root].prim >= 0;
+  std::vector<DNode<R>> dn(single_leaf ? 1 : n_inner);
+  auto set_box = [&](DNode<R>& d, int side, const rtc_bvh_node& c) {
+    R lox = round_down<R>(c.bmin[0]), hix = round_up<R>(c.bmax[0]);
+    R loy = round_down<R>(c.bmin[1]), hiy = round_up<R>(c.bmax[1]);
+    R loz = round_down<R>(c.bmin[2]), hiz = round_up<R>(c.bmax[2]);
+    V4<R>& nxy = side == 0 ? d.n0 : d.n1;
+    nxy.x = lox; nxy.y = hix; nxy.z = loy; nxy.w = hiy;
+    if (side == 0) { d.nz.x = loz; d.nz.y = hiz; } else { d.nz.z = loz; d.nz.w = hiz; }
+  };
+  if (single_leaf) {
+    std::memset(&dn[0], 0, sizeof(DNode<R>));
+    set_box(dn[0], 0, nodes[ctx->root]);
+    dn[0].left = leaf_ref(ctx->root);
+    dn[0].right = REF_EMPTY;
+    ctx->root_node = 0;
+  } else {
+    for (int32_t i = 0; i < nn; i++) {
+      if (inner_idx[i] < 0) continue;
+      DNode<R>& d = dn[inner_idx[i]];
+      std::memset(&d, 0, sizeof(d));
+      set_box(d, 0, nodes[nodes[i].left]);
+      set_box(d, 1, nodes[nodes[i].right]);
+      d.left = child_ref(nodes[i].left);
+      d.right = child_ref(nodes[i].right);
+    }
+    ctx->root_node = (uint32_t)inner_idx[ctx->root];
+  }
+
+  std::vector<DPrim<R>> dp(n);
+  std::vector<DMat<R>> dm(n);
+  std::vector<int32_t> aux(n, -1), prim_id(n), id_to_slot(n);
+  std::vector<uint32_t> prim_ref(n);
+  for (int32_t i = 0; i < nn; i++) {
+    if (leaf_slot[i] < 0) continue;
+    prim_ref[leaf_slot[i]] = leaf_ref(i);
+  }
+  for (int32_t s = 0; s < n; s++) {
+    int32_t p = slot_prim[s];
+    prim_id[s] = p;
+    id_to_slot[p] = s;
+    const double* g = &ctx->geom[(size_t)p * RTC_GEOM_STRIDE];
+    DPrim<R>& d = dp[s];
+    std::memset(&d, 0, sizeof(d));
+    uint8_t k = ctx->kind[p], f = ctx->flags[p];
+    if (k == RTC_KIND_TRIANGLE) {
+      d.a.x = (R)g[0]; d.a.y = (R)g[1]; d.a.z = (R)g[2]; d.a.w = (R)g[9];
+      d.b.x = (R)g[3]; d.b.y = (R)g[4]; d.b.z = (R)g[5]; d.b.w = (R)g[10];
+      d.c.x = (R)g[6]; d.c.y = (R)g[7]; d.c.z = (R)g[8]; d.c.w = (R)g[11];
+      if ((f & RTC_FLAG_VNORMALS) && ctx->xform[p] >= 0) aux[s] = ctx->xform[p] | (int32_t)REF_VNORMALS_AUX;
+    } else {
+      d.a.x = (R)g[0]; d.a.y = (R)g[1]; d.a.z = (R)g[2]; d.a.w = (R)g[3];
+      if (k == RTC_KIND_SPHERE && (f & RTC_FLAG_TRANSFORMED) && ctx->xform[p] >= 0) aux[s] = ctx->xform[p];
+    }
+    const double* m = &ctx->material[(size_t)p * RTC_MATERIAL_STRIDE];
+    DMat<R>& dmat = dm[s];
+    bool reflective = m[13] > 0;  // Primitive.IsReflective (Primitive.cs:106): Specular/Refraction read black otherwise
+    dmat.emis_ior = V4<R>{(R)m[0], (R)m[1], (R)m[2], (R)m[12]};
+    dmat.diff_shin = V4<R>{(R)m[3], (R)m[4], (R)m[5], (R)m[13]};
+    dmat.spec = reflective ? V4<R>{(R)m[6], (R)m[7], (R)m[8], R(0)} : V4<R>{R(0), R(0), R(0), R(0)};
+    dmat.refr = reflective ? V4<R>{(R)m[9], (R)m[10], (R)m[11], R(0)} : V4<R>{R(0), R(0), R(0), R(0)};
+  }
+  std::vector<DXform<R>> dx(std::max(1, ctx->n_xforms));
+  std::memset(dx.data(), 0, dx.size() * sizeof(DXform<R>));
+  for (int32_t j = 0; j < ctx->n_xforms; j++) {
+    const double* x = &ctx->xforms[(size_t)j * RTC_XFORM_STRIDE];
+    for (int mtx = 0; mtx < 3; mtx++)
+      for (int row = 0; row < 3; row++) {
+        const double* r = x + mtx * 16 + row * 4;
+        dx[j].r[mtx * 3 + row] = V4<R>{(R)r[0], (R)r[1], (R)r[2], (R)r[3]};
+      }
+  }
+  // vertex-normal triangles keep n0,n1,n2 in the first 9 doubles of their row
+  for (int32_t s = 0; s < n; s++) {
+    if (aux[s] >= 0 && (aux[s] & (int32_t)REF_VNORMALS_AUX)) {
+      int32_t j = aux[s] & 0x3FFFFFFF;
+      const double* x = &ctx->xforms[(size_t)j * RTC_XFORM_STRIDE];
+      for (int k2 = 0; k2 < 3; k2++) dx[j].r[k2] = V4<R>{(R)x[k2 * 3], (R)x[k2 * 3 + 1], (R)x[k2 * 3 + 2], R(0)};
+    }
+  }
+
+  free_scene_device(ctx);
+  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return e;
+    return bytes ? cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+  };
+  CU(up(&ctx->d_nodes, dn.data(), dn.size() * sizeof(DNode<R>)));
+  CU(up(&ctx->d_prims, dp.data(), dp.size() * sizeof(DPrim<R>)));
+  CU(up(&ctx->d_mats, dm.data(), dm.size() * sizeof(DMat<R>)));
+  CU(up(&ctx->d_xforms, dx.data(), dx.size() * sizeof(DXform<R>)));
+  CU(up((void**)&ctx->d_aux, aux.data(), aux.size() * sizeof(int32_t)));
+  CU(up((void**)&ctx->d_prim_id, prim_id.data(), prim_id.size() * sizeof(int32_t)));
+  CU(up((void**)&ctx->d_id_to_slot, id_to_slot.data(), id_to_slot.size() * sizeof(int32_t)));
+  CU(up((void**)&ctx->d_prim_ref, prim_ref.data(), prim_ref.size() * sizeof(uint32_t)));
+  CU(cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope
+  return RTC_OK;
+}
+
+int ready(rtc_ctx* ctx, bool need_camera) {
+  if (!ctx->scene_set) return fail(ctx, RTC_ERR_STATE, "no scene uploaded (rtc_upload_scene)");
+  if (!ctx->bvh_set) return fail(ctx, RTC_ERR_STATE, "no BVH (rtc_upload_bvh or rtc_build_bvh)");
+  if (need_camera && !ctx->camera_set) return fail(ctx, RTC_ERR_STATE, "no camera (rtc_set_camera)");
+  if (need_camera && !ctx->params_set) return fail(ctx, RTC_ERR_STATE, "no render parameters (rtc_set_params)");
+  return RTC_OK;
+}
+
+cudaEvent_t get_event(rtc_ctx* c) {
+  if (!c->free_events.empty()) {
+    cudaEvent_t e = c->free_events.back();
+    c->free_events.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void drain_timing(rtc_ctx* c) {
+  for (TimedLaunch& t : c->pending) {
+    float ms = 0;
+    if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) c->stats.ms[t.kind] += ms;
+    c->free_events.push_back(t.a);
+    c->free_events.push_back(t.b);
+  }
+  c->pending.clear();
+}
+
+struct Timed {
+  rtc_ctx* c;
+  int kind;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Timed(rtc_ctx* ctx, int k) : c(ctx), kind(k) {
+    c->stats.launches[k]++;
+    if (c->timing) {
+      a = get_event(c);
+      b = get_event(c);
+      cudaEventRecord(a, c->stream);
+    }
+  }
+  ~Timed() {
+    if (c->timing) {
+      cudaEventRecord(b, c->stream);
+      c->pending.push_back({a, b, kind});
+      if (c->pending.size() > 8192) drain_timing(c);
+    }
+  }
+};
+
+// One wavefront over `band`: raygen, (trace, shade, compact) x (recursion+1), then accumulate or export.
+template <typename R>
+int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb, bool debug) {
+  LaunchCfg cfg{ctx->stream, ctx->sm_count, ctx->counters};
+  SceneView<R> sv = scene_view<R>(ctx);
+  PathView<R> pv = path_view<R>(ctx);
+  if (debug) {
+    pv.dbg_type = ctx->d_dbg_type;
+    pv.dbg_fresnel = (R*)ctx->d_dbg_fresnel;
+  }
+  CameraView<R> cv = camera_view<R>(ctx->cam);
+  ParamsView<R> par = params_view<R>(ctx->par);
+  {
+    Timed t(ctx, RTC_K_RAYGEN);
+    CU(Kernels<R>::raygen(cfg, cv, par, band, pv));
+  }
+  ctx->stats.paths += band.n_paths;
+  const int bounces = std::max(0, ctx->par.recursion) + 1;
+  for (int i = 0; i < bounces; i++) {
+    const int q = i & 1;
+    const int cur = i & 1, prev = cur ^ 1;  // raygen seeds buffer 1 as the "previous hit" of bounce 0
+    const bool ident = (i == 0);
+    {
+      Timed t(ctx, RTC_K_TRACE);
+      CU(Kernels<R>::trace(cfg, sv, pv, q, prev, cur, ident));
+    }
+    {
+      Timed t(ctx, RTC_K_SHADE);
+      CU(Kernels<R>::shade(cfg, sv, par, band, pv, q, cur, i, ident));
+    }
+    {
+      Timed t(ctx, RTC_K_COMPACT);
+      CU(Kernels<R>::compact(cfg, pv, q, ident));
+    }
+  }
+  if (accumulate) {
+    Timed t(ctx, RTC_K_ACCUMULATE);
+    CU(Kernels<R>::accumulate(cfg, par, band, pv, ctx->d_rgb, ctx->d_samples, ctx->d_misses));
+  } else if (d_out_rgb) {
+    CU(Kernels<R>::export_radiance(cfg, band, par, pv, d_out_rgb));
+  }
+  return RTC_OK;
+}
+
+template <typename R>
+int render_rect(rtc_ctx* ctx, int x0, int y0, int x1, int y1, uint32_t first_sample, uint32_t n_samples, bool accumulate,
+                double* d_out_rgb) {
+  const int64_t rw = x1 - x0;
+  const int64_t cap = std::max<int64_t>(ctx->max_paths, rw);
+  int rc = ensure_pool(ctx, cap);
+  if (rc) return rc;
+  int64_t rows_per_band = std::max<int64_t>(1, std::min<int64_t>(y1 - y0, cap / rw));
+  for (int ya = y0; ya < y1; ya += (int)rows_per_band) {
+    int yb = (int)std::min<int64_t>(y1, ya + rows_per_band);
+    int64_t npix = rw * (yb - ya);
+    uint32_t s_chunk = (uint32_t)std::max<int64_t>(1, cap / npix);
+    for (uint32_t s = 0; s < n_samples; s += s_chunk) {
+      Band b;
+      b.x0 = x0; b.x1 = x1; b.y0 = ya; b.y1 = yb;
+      b.first_sample = first_sample + s;
+      b.n_samples = std::min(s_chunk, n_samples - s);
+      b.n_pix = (uint32_t)npix;
+      b.n_paths = (uint32_t)(npix * b.n_samples);
+      rc = run_band<R>(ctx, b, accumulate, d_out_rgb, false);
+      if (rc) return rc;
+    }
+  }
+  return RTC_OK;
+}
+
+int ensure_accum(rtc_ctx* ctx) {
+  int w = ctx->par.width, h = ctx->par.height;
+  if (ctx->d_rgb && ctx->acc_w == w && ctx->acc_h == h) return RTC_OK;
+  free_dev_t(ctx->d_rgb);
+  free_dev_t(ctx->d_samples);
+  free_dev_t(ctx->d_misses);
+  size_t n = (size_t)w * h;
+  CU(cudaMalloc((void**)&ctx->d_rgb, n * 3 * sizeof(double)));
+  CU(cudaMalloc((void**)&ctx->d_samples, n * sizeof(uint32_t)));
+  CU(cudaMalloc((void**)&ctx->d_misses, n * sizeof(uint32_t)));
+  CU(cudaMemsetAsync(ctx->d_rgb, 0, n * 3 * sizeof(double), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_samples, 0, n * sizeof(uint32_t), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_misses, 0, n * sizeof(uint32_t), ctx->stream));
+  ctx->acc_w = w;
+  ctx->acc_h = h;
+  return RTC_OK;
+}
+
+template <typename R>
+int trace_batch(rtc_ctx* ctx, int64_t n, const rtc_ray* rays, const rtc_hit* skip, rtc_hit* out) {
+  const int64_t cap = ctx->max_paths;
+  int rc = ensure_pool(ctx, cap);
+  if (rc) return rc;
+  if (!ctx->d_skip_pos) CU(cudaMalloc(&ctx->d_skip_pos, rsize(ctx) * 4 * ctx->pool_cap));
+  if (ctx->stage_cap < std::min(cap, n)) {
+    free_dev_t(ctx->d_rays);
+    free_dev_t(ctx->d_skip);
+    free_dev_t(ctx->d_hits);
+    ctx->stage_cap = std::min(cap, n);
+    CU(cudaMalloc((void**)&ctx->d_rays, sizeof(rtc_ray) * ctx->stage_cap));
+    CU(cudaMalloc((void**)&ctx->d_skip, sizeof(rtc_hit) * ctx->stage_cap));
+    CU(cudaMalloc((void**)&ctx->d_hits, sizeof(rtc_hit) * ctx->stage_cap));
+  }
+  LaunchCfg cfg{ctx->stream, ctx->sm_count, ctx->counters};
+  SceneView<R> sv = scene_view<R>(ctx);
+  PathView<R> pv = path_view<R>(ctx);
+  pv.skip_pos = (V4<R>*)ctx->d_skip_pos;
+  for (int64_t off = 0; off < n; off += ctx->stage_cap) {
+    int64_t m = std::min(ctx->stage_cap, n - off);
+    CU(cudaMemcpyAsync(ctx->d_rays, rays + off, sizeof(rtc_ray) * m, cudaMemcpyHostToDevice, ctx->stream));
+    if (skip) CU(cudaMemcpyAsync(ctx->d_skip, skip + off, sizeof(rtc_hit) * m, cudaMemcpyHostToDevice, ctx->stream));
+    CU(Kernels<R>::import_rays(cfg, sv, m, ctx->d_rays, skip ? ctx->d_skip : nullptr, ctx->d_id_to_slot, pv, 1));
+    {
+      Timed t(ctx, RTC_K_TRACE);
+      CU(Kernels<R>::trace(cfg, sv, pv, 0, 1, 0, true));
+    }
+    ctx->stats.rays += (uint64_t)m;
+    CU(Kernels<R>::export_hits(cfg, sv, m, pv, 0, ctx->d_hits));
+    CU(cudaMemcpyAsync(out + off, ctx->d_hits, sizeof(rtc_hit) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return RTC_OK;
+}
+
+int fetch_device_counters(rtc_ctx* ctx, Control* host) {
+  if (!ctx->d_ctl) {
+    std::memset(host, 0, sizeof(*host));
+    return RTC_OK;
+  }
+  CU(cudaMemcpyAsync(host, ctx->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RTC_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int rtc_abi_version(void) { return RTC_ABI_VERSION; }
+
+int rtc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int rtc_create(int device, int precision, rtc_ctx** out) {
+  if (!out) return RTC_ERR_INVALID;
+  *out = nullptr;
+  if (precision != RTC_F32 && precision != RTC_F64) {
+    g_create_error = "precision must be RTC_F32 or RTC_F64";
+    return RTC_ERR_INVALID;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_error = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                     "); librtcore_b200 has no CPU fallback";
+    cudaGetLastError();
+    return RTC_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    g_create_error = "device index out of range";
+    return RTC_ERR_INVALID;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return RTC_ERR_CUDA;
+  }
+  rtc_ctx* ctx = new rtc_ctx();
+  ctx->device = device;
+  ctx->precision = precision;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+    delete ctx;
+    return RTC_ERR_CUDA;
+  }
+  *out = ctx;
+  return RTC_OK;
+}
+
+void rtc_destroy(rtc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  rtc_comm_destroy(ctx);
+  drain_timing(ctx);
+  for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+  free_scene_device(ctx);
+  free_pool(ctx);
+  free_dev_t(ctx->d_ctl);
+  free_dev_t(ctx->d_rays);
+  free_dev_t(ctx->d_skip);
+  free_dev_t(ctx->d_hits);
+  free_dev_t(ctx->d_rgb);
+  free_dev_t(ctx->d_samples);
+  free_dev_t(ctx->d_misses);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* rtc_last_error(rtc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rtc_set_option(rtc_ctx* ctx, int option, int64_t value) {
+  if (!ctx) return RTC_ERR_INVALID;
+  switch (option) {
+    case RTC_OPT_KERNEL_TIMING: ctx->timing = value != 0; return RTC_OK;
+    case RTC_OPT_COUNTERS: ctx->counters = value != 0; return RTC_OK;
+    case RTC_OPT_MAX_PATHS:
+      if (value < 1024 || value > (int64_t)1 << 28) return fail(ctx, RTC_ERR_INVALID, "max paths must be in [1024, 2^28]");
+      if (value != ctx->max_paths) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        free_pool(ctx);
+        free_dev_t(ctx->d_rays);
+        free_dev_t(ctx->d_skip);
+        free_dev_t(ctx->d_hits);
+        ctx->stage_cap = 0;
+        ctx->max_paths = value;
+      }
+      return RTC_OK;
+    default: return fail(ctx, RTC_ERR_INVALID, "unknown option");
+  }
+}
+
+int rtc_upload_scene(rtc_ctx* ctx, const rtc_scene_desc* s) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!s || s->n_prims < 0 || s->n_xforms < 0) return fail(ctx, RTC_ERR_INVALID, "scene description is null or has negative counts");
+  if (s->n_prims > 0 && (!s->kind || !s->flags || !s->geom || !s->material)) return fail(ctx, RTC_ERR_INVALID, "scene arrays must not be null");
+  if (s->n_xforms > 0 && (!s->xform || !s->xforms)) return fail(ctx, RTC_ERR_INVALID, "xform arrays must not be null when n_xforms > 0");
+  const size_t n = (size_t)s->n_prims;
+  for (size_t i = 0; i < n; i++) {
+    if (s->kind[i] > RTC_KIND_PLANE) return fail(ctx, RTC_ERR_INVALID, "unknown primitive kind at index " + std::to_string(i));
+    if (s->xform && s->xform[i] >= s->n_xforms) return fail(ctx, RTC_ERR_INVALID, "xform index out of range at primitive " + std::to_string(i));
+  }
+  ctx->n_prims = s->n_prims;
+  ctx->n_xforms = s->n_xforms;
+  ctx->kind.assign(s->kind, s->kind + n);
+  ctx->flags.assign(s->flags, s->flags + n);
+  ctx->geom.assign(s->geom, s->geom + n * RTC_GEOM_STRIDE);
+  ctx->material.assign(s->material, s->material + n * RTC_MATERIAL_STRIDE);
+  if (s->xform)
+    ctx->xform.assign(s->xform, s->xform + n);
+  else
+    ctx->xform.assign(n, -1);
+  if (s->n_xforms > 0)
+    ctx->xforms.assign(s->xforms, s->xforms + (size_t)s->n_xforms * RTC_XFORM_STRIDE);
+  else
+    ctx->xforms.clear();
+  ctx->scene_set = true;
+  ctx->bvh_set = false;  // Scene.AddPrimitive -> ResetAccelerator (Scene.cs:58-63)
+  ctx->nodes.clear();
+  ctx->root = -1;
+  return RTC_OK;
+}
+
+static int finish_bvh(rtc_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  int rc = ctx->precision == RTC_F64 ? build_device_scene<double>(ctx) : build_device_scene<float>(ctx);
+  ctx->bvh_set = rc == RTC_OK;
+  return rc;
+}
+
+int rtc_upload_bvh(rtc_ctx* ctx, int32_t n_nodes, const rtc_bvh_node* nodes, int32_t root) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!ctx->scene_set) return fail(ctx, RTC_ERR_STATE, "upload the scene before the BVH");
+  if (ctx->n_prims == 0) return fail(ctx, RTC_ERR_INVALID, "scene has no primitives");
+  if (!nodes || n_nodes <= 0) return fail(ctx, RTC_ERR_INVALID, "nodes is null or empty");
+  ctx->nodes.assign(nodes, nodes + n_nodes);
+  ctx->root = root;
+  return finish_bvh(ctx);
+}
+
+int rtc_build_bvh(rtc_ctx* ctx) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!ctx->scene_set) return fail(ctx, RTC_ERR_STATE, "upload the scene before building the BVH");
+  if (ctx->n_prims == 0) return fail(ctx, RTC_ERR_INVALID, "scene has no primitives");
+  rtc_scene_desc d;
+  d.n_prims = ctx->n_prims;
+  d.n_xforms = ctx->n_xforms;
+  d.kind = ctx->kind.data();
+  d.flags = ctx->flags.data();
+  d.geom = ctx->geom.data();
+  d.xform = ctx->xform.data();
+  d.xforms = ctx->xforms.empty() ? nullptr : ctx->xforms.data();
+  d.material = ctx->material.data();
+  const int n = d.n_prims;
+  std::vector<double> lo((size_t)n * 3), hi((size_t)n * 3);
+  for (int i = 0; i < n; i++) rtcore::DescPrimitiveBounds(d, i, &lo[(size_t)i * 3], &hi[(size_t)i * 3]);
+  int threads = (int)std::thread::hardware_concurrency();
+  ctx->root = rtcore::BuildBVH(n, lo.data(), hi.data(), ctx->nodes, threads > 0 ? threads : 1);
+  return finish_bvh(ctx);
+}
+
+int rtc_get_bvh_size(rtc_ctx* ctx, int32_t* n_nodes, int32_t* root) {
+  if (!ctx || !n_nodes || !root) return RTC_ERR_INVALID;
+  if (!ctx->bvh_set) return fail(ctx, RTC_ERR_STATE, "no BVH");
+  *n_nodes = (int32_t)ctx->nodes.size();
+  *root = ctx->root;
+  return RTC_OK;
+}
+
+int rtc_get_bvh(rtc_ctx* ctx, int32_t capacity, rtc_bvh_node* nodes) {
+  if (!ctx || !nodes) return RTC_ERR_INVALID;
+  if (!ctx->bvh_set) return fail(ctx, RTC_ERR_STATE, "no BVH");
+  if (capacity < (int32_t)ctx->nodes.size()) return fail(ctx, RTC_ERR_INVALID, "capacity too small");
+  std::memcpy(nodes, ctx->nodes.data(), ctx->nodes.size() * sizeof(rtc_bvh_node));
+  return RTC_OK;
+}
+
+int rtc_set_camera(rtc_ctx* ctx, const rtc_camera* camera) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!camera) return fail(ctx, RTC_ERR_INVALID, "camera is null");
+  if (camera->kind != RTC_CAMERA_FRUSTUM && camera->kind != RTC_CAMERA_ORTHO) return fail(ctx, RTC_ERR_INVALID, "unknown camera kind");
+  ctx->cam = *camera;
+  ctx->camera_set = true;
+  return RTC_OK;
+}
+
+int rtc_set_params(rtc_ctx* ctx, const rtc_params* p) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!p) return fail(ctx, RTC_ERR_INVALID, "params is null");
+  if (p->width <= 0 || p->height <= 0 || p->recursion < 0) return fail(ctx, RTC_ERR_INVALID, "width/height must be positive and recursion non-negative");
+  if ((int64_t)p->width * p->height > (int64_t)1 << 30) return fail(ctx, RTC_ERR_UNSUPPORTED, "image larger than 2^30 pixels");
+  ctx->par = *p;
+  ctx->params_set = true;
+  cudaSetDevice(ctx->device);
+  return ensure_accum(ctx);
+}
+
+int rtc_trace_closest(rtc_ctx* ctx, int64_t n, const rtc_ray* rays, const rtc_hit* skip, rtc_hit* out) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!rays || !out))) return fail(ctx, RTC_ERR_INVALID, "rays/out must not be null");
+  int rc = ready(ctx, false);
+  if (rc) return rc;
+  if (n == 0) return RTC_OK;
+  cudaSetDevice(ctx->device);
+  return ctx->precision == RTC_F64 ? trace_batch<double>(ctx, n, rays, skip, out) : trace_batch<float>(ctx, n, rays, skip, out);
+}
+
+int rtc_camera_rays(rtc_ctx* ctx, int64_t n, const int32_t* xy, const uint32_t* sample, rtc_ray* out) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!xy || !sample || !out))) return fail(ctx, RTC_ERR_INVALID, "xy/sample/out must not be null");
+  if (!ctx->camera_set || !ctx->params_set) return fail(ctx, RTC_ERR_STATE, "camera and params must be set");
+  if (n == 0) return RTC_OK;
+  cudaSetDevice(ctx->device);
+  int32_t* dxy = nullptr;
+  uint32_t* ds = nullptr;
+  rtc_ray* dout = nullptr;
+  CU(cudaMalloc((void**)&dxy, sizeof(int32_t) * 2 * n));
+  CU(cudaMalloc((void**)&ds, sizeof(uint32_t) * n));
+  CU(cudaMalloc((void**)&dout, sizeof(rtc_ray) * n));
+  CU(cudaMemcpyAsync(dxy, xy, sizeof(int32_t) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ds, sample, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  LaunchCfg cfg{ctx->stream, ctx->sm_count, false};
+  cudaError_t e;
+  if (ctx->precision == RTC_F64)
+    e = Kernels<double>::camera_rays(cfg, camera_view<double>(ctx->cam), params_view<double>(ctx->par), n, dxy, ds, dout);
+  else
+    e = Kernels<float>::camera_rays(cfg, camera_view<float>(ctx->cam), params_view<float>(ctx->par), n, dxy, ds, dout);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, sizeof(rtc_ray) * n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dxy);
+  cudaFree(ds);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("camera_rays: ") + cudaGetErrorString(e));
+  return RTC_OK;
+}
+
+int rtc_render(rtc_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1, uint32_t first_sample, uint32_t n_samples) {
+  if (!ctx) return RTC_ERR_INVALID;
+  int rc = ready(ctx, true);
+  if (rc) return rc;
+  if (x0 < 0 || y0 < 0 || x1 > ctx->par.width || y1 > ctx->par.height || x0 >= x1 || y0 >= y1)
+    return fail(ctx, RTC_ERR_INVALID, "render rectangle is empty or outside the image");
+  if (n_samples == 0) return RTC_OK;
+  cudaSetDevice(ctx->device);
+  rc = ensure_accum(ctx);
+  if (rc) return rc;
+  return ctx->precision == RTC_F64 ? render_rect<double>(ctx, x0, y0, x1, y1, first_sample, n_samples, true, nullptr)
+                                   : render_rect<float>(ctx, x0, y0, x1, y1, first_sample, n_samples, true, nullptr);
+}
+
+int rtc_sync(rtc_ctx* ctx) {
+  if (!ctx) return RTC_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  drain_timing(ctx);
+  return RTC_OK;
+}
+
+int rtc_clear_accum(rtc_ctx* ctx) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!ctx->params_set) return fail(ctx, RTC_ERR_STATE, "no render parameters (rtc_set_params)");
+  cudaSetDevice(ctx->device);
+  int rc = ensure_accum(ctx);
+  if (rc) return rc;
+  size_t n = (size_t)ctx->acc_w * ctx->acc_h;
+  CU(cudaMemsetAsync(ctx->d_rgb, 0, n * 3 * sizeof(double), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_samples, 0, n * sizeof(uint32_t), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_misses, 0, n * sizeof(uint32_t), ctx->stream));
+  return RTC_OK;
+}
+
+int rtc_read_accum(rtc_ctx* ctx, double* rgb_sum, uint32_t* samples, uint32_t* misses) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!ctx->d_rgb) return fail(ctx, RTC_ERR_STATE, "no accumulation buffer (rtc_set_params)");
+  cudaSetDevice(ctx->device);
+  size_t n = (size_t)ctx->acc_w * ctx->acc_h;
+  if (rgb_sum) CU(cudaMemcpyAsync(rgb_sum, ctx->d_rgb, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (samples) CU(cudaMemcpyAsync(samples, ctx->d_samples, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (misses) CU(cudaMemcpyAsync(misses, ctx->d_misses, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  drain_timing(ctx);
+  return RTC_OK;
+}
+
+int rtc_write_accum(rtc_ctx* ctx, const double* rgb_sum, const uint32_t* samples, const uint32_t* misses) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!rgb_sum || !samples || !misses) return fail(ctx, RTC_ERR_INVALID, "accumulation planes must not be null");
+  if (!ctx->d_rgb) return fail(ctx, RTC_ERR_STATE, "no accumulation buffer (rtc_set_params)");
+  cudaSetDevice(ctx->device);
+  size_t n = (size_t)ctx->acc_w * ctx->acc_h;
+  CU(cudaMemcpyAsync(ctx->d_rgb, rgb_sum, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_samples, samples, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_misses, misses, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RTC_OK;
+}
+
+int rtc_accum_device_ptrs(rtc_ctx* ctx, void** rgb_sum, void** samples, void** misses) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!ctx->d_rgb) return fail(ctx, RTC_ERR_STATE, "no accumulation buffer (rtc_set_params)");
+  if (rgb_sum) *rgb_sum = ctx->d_rgb;
+  if (samples) *samples = ctx->d_samples;
+  if (misses) *misses = ctx->d_misses;
+  return RTC_OK;
+}
+
+int rtc_tonemap_argb(rtc_ctx* ctx, double exposure, const double back_rgb[3], double back_a, uint32_t* argb) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!back_rgb || !argb) return fail(ctx, RTC_ERR_INVALID, "back_rgb/argb must not be null");
+  if (!ctx->d_rgb) return fail(ctx, RTC_ERR_STATE, "no accumulation buffer (rtc_set_params)");
+  cudaSetDevice(ctx->device);
+  int32_t n = ctx->acc_w * ctx->acc_h;
+  uint32_t* d = nullptr;
+  CU(cudaMalloc((void**)&d, sizeof(uint32_t) * (size_t)n));
+  cudaError_t e = launch_tonemap(ctx->stream, n, ctx->d_rgb, ctx->d_samples, ctx->d_misses, exposure, back_rgb[0], back_rgb[1], back_rgb[2], back_a, d);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(argb, d, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("tonemap: ") + cudaGetErrorString(e));
+  return RTC_OK;
+}
+
+int rtc_render_samples(rtc_ctx* ctx, uint32_t sample, double* out_rgb) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!out_rgb) return fail(ctx, RTC_ERR_INVALID, "out_rgb must not be null");
+  int rc = ready(ctx, true);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  size_t n = (size_t)ctx->par.width * ctx->par.height;
+  double* d = nullptr;
+  CU(cudaMalloc((void**)&d, n * 3 * sizeof(double)));
+  rc = ctx->precision == RTC_F64 ? render_rect<double>(ctx, 0, 0, ctx->par.width, ctx->par.height, sample, 1, false, d)
+                                 : render_rect<float>(ctx, 0, 0, ctx->par.width, ctx->par.height, sample, 1, false, d);
+  cudaError_t e = cudaSuccess;
+  if (rc == RTC_OK) e = cudaMemcpyAsync(out_rgb, d, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("render_samples: ") + cudaGetErrorString(e));
+  return RTC_OK;
+}
+
+int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t capacity, rtc_debug_ray* out, int32_t* n_out) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!out || !n_out || capacity <= 0) return fail(ctx, RTC_ERR_INVALID, "out/n must not be null and capacity positive");
+  int rc = ready(ctx, true);
+  if (rc) return rc;
+  if (x < 0 || y < 0 || x >= ctx->par.width || y >= ctx->par.height) return fail(ctx, RTC_ERR_INVALID, "pixel outside the image");
+  cudaSetDevice(ctx->device);
+  rc = ensure_pool(ctx, ctx->max_paths);
+  if (rc) return rc;
+  if (!ctx->d_dbg_type) {
+    CU(cudaMalloc((void**)&ctx->d_dbg_type, sizeof(int32_t) * 32));
+    CU(cudaMalloc(&ctx->d_dbg_fresnel, sizeof(double) * 32));
+  }
+  // Replay the one path bounce by bounce: a band of one pixel, with recursion clamped to i so that every prefix
+  // of the path ends in a recorded state. Cheap (<= recursion+1 single-thread wavefronts) and exact.
+  const int full = ctx->par.recursion;
+  *n_out = 0;
+  rtc_params saved = ctx->par;
+  std::vector<rtc_hit> hits(1);
+  for (int i = 0; i <= full && i < capacity; i++) {
+    Band b;
+    b.x0 = x; b.x1 = x + 1; b.y0 = y; b.y1 = y + 1;
+    b.first_sample = sample; b.n_samples = 1; b.n_pix = 1; b.n_paths = 1;
+    // run bounces 0..i with the real recursion limit, but stop after bounce i
+    LaunchCfg cfg{ctx->stream, ctx->sm_count, false};
+    int32_t type = 0;
+    double fres = 0;
+    float fres32 = 0;
+    uint32_t alive = 0;
+    auto run = [&](auto tag) -> int {
+      using R = decltype(tag);
+      SceneView<R> sv = scene_view<R>(ctx);
+      PathView<R> pv = path_view<R>(ctx);
+      pv.dbg_type = ctx->d_dbg_type;
+      pv.dbg_fresnel = (R*)ctx->d_dbg_fresnel;
+      CU(Kernels<R>::raygen(cfg, camera_view<R>(ctx->cam), params_view<R>(ctx->par), b, pv));
+      int cur = 0;
+      for (int k = 0; k <= i; k++) {
+        cur = k & 1;
+        CU(Kernels<R>::trace(cfg, sv, pv, k & 1, cur ^ 1, cur, k == 0));
+        CU(Kernels<R>::shade(cfg, sv, params_view<R>(ctx->par), b, pv, k & 1, cur, k, k == 0));
+        if (k < i) CU(Kernels<R>::compact(cfg, pv, k & 1, k == 0));
+      }
+      if (!ctx->d_hits) {
+        CU(cudaMalloc((void**)&ctx->d_hits, sizeof(rtc_hit) * 1024));
+      }
+      CU(Kernels<R>::export_hits(cfg, sv, 1, pv, cur, ctx->d_hits));
+      CU(cudaMemcpyAsync(hits.data(), ctx->d_hits, sizeof(rtc_hit), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(&type, ctx->d_dbg_type, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      if (sizeof(R) == 8)
+        CU(cudaMemcpyAsync(&fres, ctx->d_dbg_fresnel, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      else
+        CU(cudaMemcpyAsync(&fres32, ctx->d_dbg_fresnel, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(&alive, ctx->d_queue[i & 1], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (sizeof(R) == 4) fres = (double)fres32;
+      return RTC_OK;
+    };
+    rc = ctx->precision == RTC_F64 ? run(double()) : run(float());
+    if (rc) {
+      ctx->par = saved;
+      return rc;
+    }
+    out[i].hit = hits[0];
+    out[i].type = type;
+    out[i].pad = 0;
+    out[i].fresnel_ratio = fres;
+    *n_out = i + 1;
+    if (alive & Q_DEAD) break;  // the path ended at bounce i
+  }
+  ctx->par = saved;
+  return RTC_OK;
+}
+
+int rtc_get_stats(rtc_ctx* ctx, rtc_stats* stats) {
+  if (!ctx || !stats) return RTC_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  Control h;
+  int rc = fetch_device_counters(ctx, &h);
+  if (rc) return rc;
+  drain_timing(ctx);
+  *stats = ctx->stats;
+  stats->rays += h.rays;
+  stats->nodes_visited = h.nodes_visited;
+  stats->prims_tested = h.prims_tested;
+  return RTC_OK;
+}
+
+int rtc_reset_stats(rtc_ctx* ctx) {
+  if (!ctx) return RTC_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  drain_timing(ctx);
+  std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+  if (ctx->d_ctl) CU(cudaMemset(ctx->d_ctl, 0, sizeof(Control)));
+  return RTC_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------
+int rtc_comm_unique_id(void* id128) {
+  if (!id128) return RTC_ERR_INVALID;
+  if (!g_nccl.load(g_create_error)) return RTC_ERR_NCCL;
+  NcclId id;
+  int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) {
+    g_create_error = "ncclGetUniqueId failed";
+    return RTC_ERR_NCCL;
+  }
+  std::memcpy(id128, &id, sizeof(id));
+  return RTC_OK;
+}
+
+int rtc_comm_init(rtc_ctx* ctx, int32_t nranks, int32_t rank, const void* id128) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, RTC_ERR_INVALID, "bad rank / nranks / id");
+  if (!g_nccl.load(ctx->err)) return RTC_ERR_NCCL;
+  cudaSetDevice(ctx->device);
+  rtc_comm_destroy(ctx);
+  NcclId id;
+  std::memcpy(&id, id128, sizeof(id));
+  int r = g_nccl.CommInitRank(&ctx->nccl_comm, nranks, id, rank);
+  if (r != 0) return fail(ctx, RTC_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+  ctx->nranks = nranks;
+  ctx->rank = rank;
+  return RTC_OK;
+}
+
+int rtc_reduce_accum(rtc_ctx* ctx, int32_t root) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!ctx->nccl_comm) return fail(ctx, RTC_ERR_STATE, "rtc_comm_init has not been called");
+  if (!ctx->d_rgb) return fail(ctx, RTC_ERR_STATE, "no accumulation buffer (rtc_set_params)");
+  if (root >= ctx->nranks) return fail(ctx, RTC_ERR_INVALID, "root out of range");
+  cudaSetDevice(ctx->device);
+  size_t n = (size_t)ctx->acc_w * ctx->acc_h;
+  int r = g_nccl.GroupStart();
+  if (r == 0) {
+    if (root < 0) {
+      r = g_nccl.AllReduce(ctx->d_rgb, ctx->d_rgb, n * 3, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+      if (r == 0) r = g_nccl.AllReduce(ctx->d_samples, ctx->d_samples, n, kNcclUint32, kNcclSum, ctx->nccl_comm, ctx->stream);
+      if (r == 0) r = g_nccl.AllReduce(ctx->d_misses, ctx->d_misses, n, kNcclUint32, kNcclSum, ctx->nccl_comm, ctx->stream);
+    } else {
+      r = g_nccl.Reduce(ctx->d_rgb, ctx->d_rgb, n * 3, kNcclFloat64, kNcclSum, root, ctx->nccl_comm, ctx->stream);
+      if (r == 0) r = g_nccl.Reduce(ctx->d_samples, ctx->d_samples, n, kNcclUint32, kNcclSum, root, ctx->nccl_comm, ctx->stream);
+      if (r == 0) r = g_nccl.Reduce(ctx->d_misses, ctx->d_misses, n, kNcclUint32, kNcclSum, root, ctx->nccl_comm, ctx->stream);
+    }
+    int r2 = g_nccl.GroupEnd();
+    if (r == 0) r = r2;
+  }
+  if (r != 0) return fail(ctx, RTC_ERR_NCCL, std::string("nccl reduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+  return RTC_OK;
+}
+
+int rtc_comm_destroy(rtc_ctx* ctx) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+  ctx->nccl_comm = nullptr;
+  ctx->nranks = 1;
+  ctx->rank = 0;
+  return RTC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1102 @@
+// rtc_device.cuh — the wavefront path tracer's device code, templated on the arithmetic type R.
+//
+// R = double (kernels_f64.cu, compiled -fmad=false): a restatement of the reference's f64 arithmetic, operation by
+//     operation, with an explicit fma() exactly where the reference's AVX path fuses (SIMDHelpers.Cross, the
+//     Triangle/Sphere position FMAs). Reference files are cited per function (paths relative to RaytracerCore/).
+// R = float  (kernels_f32.cu, compiled with the default -fmad=true): same algorithm, throughput-oriented forms of
+//     the box and sphere tests, tolerance 1e-4 against the f64 oracle.
+#pragma once
+#include <math_constants.h>
+
+#include <type_traits>
+
+#include "rtc_internal.h"
+
+namespace rtc {
+
+// ---------------------------------------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+struct Num;
+template <>
+struct Num<float> {
+  static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+  static __device__ __forceinline__ float nan() { return CUDART_NAN_F; }
+  static constexpr bool is_f64 = false;
+};
+template <>
+struct Num<double> {
+  static __device__ __forceinline__ double inf() { return CUDART_INF; }
+  static __device__ __forceinline__ double nan() { return CUDART_NAN; }
+  static constexpr bool is_f64 = true;
+};
+
+__device__ __forceinline__ float rfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double rfma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float rsqrt_(float a) { return sqrtf(a); }
+__device__ __forceinline__ double rsqrt_(double a) { return sqrt(a); }
+__device__ __forceinline__ float rrcp(float a) { return __frcp_rn(a); }
+__device__ __forceinline__ double rrcp(double a) { return 1.0 / a; }
+__device__ __forceinline__ float rpow(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double rpow(double a, double b) { return pow(a, b); }
+__device__ __forceinline__ float racos(float a) { return acosf(a); }
+__device__ __forceinline__ double racos(double a) { return acos(a); }
+__device__ __forceinline__ void rsincos(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void rsincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
+__device__ __forceinline__ bool rsignbit(float a) { return (__float_as_uint(a) >> 31) != 0; }
+__device__ __forceinline__ bool rsignbit(double a) { return (__double_as_longlong(a) < 0); }
+__device__ __forceinline__ bool risnan(float a) { return a != a; }
+__device__ __forceinline__ bool risnan(double a) { return a != a; }
+// MAXPD / MINPD as used by Sse2.Max/Min: (a > b) ? a : b — the second operand wins on NaN.
+template <typename R>
+__device__ __forceinline__ R sse_max(R a, R b) { return a > b ? a : b; }
+template <typename R>
+__device__ __forceinline__ R sse_min(R a, R b) { return a < b ? a : b; }
+
+__device__ __forceinline__ uint32_t code_of(float w) { return __float_as_uint(w); }
+__device__ __forceinline__ uint32_t code_of(double w) { return (uint32_t)__double_as_longlong(w); }
+__device__ __forceinline__ void set_code(float& w, uint32_t c) { w = __uint_as_float(c); }
+__device__ __forceinline__ void set_code(double& w, uint32_t c) { w = __longlong_as_double((long long)c); }
+
+template <typename R>
+struct V3 {
+  R x, y, z;
+};
+template <typename R>
+__device__ __forceinline__ V3<R> mk3(R x, R y, R z) { V3<R> v; v.x = x; v.y = y; v.z = z; return v; }
+template <typename R>
+__device__ __forceinline__ V3<R> xyz(const V4<R>& a) { return mk3(a.x, a.y, a.z); }
+template <typename R>
+__device__ __forceinline__ V3<R> operator+(const V3<R>& a, const V3<R>& b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename R>
+__device__ __forceinline__ V3<R> operator-(const V3<R>& a, const V3<R>& b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename R>
+__device__ __forceinline__ V3<R> operator*(const V3<R>& a, R s) { return mk3(a.x * s, a.y * s, a.z * s); }
+template <typename R>
+__device__ __forceinline__ V3<R> operator/(const V3<R>& a, R s) { return mk3(a.x / s, a.y / s, a.z / s); }
+template <typename R>
+__device__ __forceinline__ V3<R> neg3(const V3<R>& a) { return mk3(-a.x, -a.y, -a.z); }
+// Vec4D.Dot (Vec4D.cs:341-347) / SIMDHelpers.Dot (SIMDHelpers.cs:70-100) with a zero W product: (x+y)+z
+template <typename R>
+__device__ __forceinline__ R dot3(const V3<R>& a, const V3<R>& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+// Vec4D.Cross (Vec4D.cs:355-364): plain products
+template <typename R>
+__device__ __forceinline__ V3<R> cross3(const V3<R>& a, const V3<R>& b) {
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// SIMDHelpers.Cross (SIMDHelpers.cs:44-61): Fma.MultiplySubtract(leftA, rightA, leftB * rightB)
+template <typename R>
+__device__ __forceinline__ V3<R> scross3(const V3<R>& a, const V3<R>& b) {
+  return mk3(rfma(a.y, b.z, -(a.z * b.y)), rfma(a.z, b.x, -(a.x * b.z)), rfma(a.x, b.y, -(a.y * b.x)));
+}
+// SIMDHelpers.Normalize (SIMDHelpers.cs:332-335): v / sqrt((x²+y²)+(z²+w²))
+template <typename R>
+__device__ __forceinline__ V3<R> normalize3(const V3<R>& a) {
+  R l = rsqrt_((a.x * a.x + a.y * a.y) + a.z * a.z);
+  return mk3(a.x / l, a.y / l, a.z / l);
+}
+// Mat4x4D * Vec4D through SIMDHelpers.MultiplyMatrixVector (Mat4x4D.cs:171-180, SIMDHelpers.cs:111-127,222-237):
+// (m0 x + m1 y) + (m2 z + m3 w), for a point (w = 1) and for a direction (w = 0).
+template <typename R>
+__device__ __forceinline__ V3<R> xf_point(const V4<R>* rows, const V3<R>& p) {
+  return mk3((rows[0].x * p.x + rows[0].y * p.y) + (rows[0].z * p.z + rows[0].w),
+             (rows[1].x * p.x + rows[1].y * p.y) + (rows[1].z * p.z + rows[1].w),
+             (rows[2].x * p.x + rows[2].y * p.y) + (rows[2].z * p.z + rows[2].w));
+}
+template <typename R>
+__device__ __forceinline__ V3<R> xf_dir(const V4<R>* rows, const V3<R>& d) {
+  return mk3((rows[0].x * d.x + rows[0].y * d.y) + rows[0].z * d.z, (rows[1].x * d.x + rows[1].y * d.y) + rows[1].z * d.z,
+             (rows[2].x * d.x + rows[2].y * d.y) + rows[2].z * d.z);
+}
+
+template <typename R>
+__device__ __forceinline__ V4<R> ldg4(const V4<R>* p) {
+  if constexpr (std::is_same<R, float>::value) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    V4<R> r; r.x = t.x; r.y = t.y; r.z = t.z; r.w = t.w;
+    return r;
+  } else {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    V4<R> r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+    return r;
+  }
+}
+template <typename R>
+__device__ __forceinline__ V4<R> ld4(const V4<R>* p) { return *p; }
+template <typename R>
+__device__ __forceinline__ void st4(V4<R>* p, R x, R y, R z, R w) {
+  V4<R> v; v.x = x; v.y = y; v.z = z; v.w = w;
+  *p = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011): counter = (pixel, sample, stage, block), key = seed. Replaces the unseeded
+// System.Random of Raytracer.cs:48 so that GPU ranks and the CPU oracle draw identical streams.
+//   stage 0      camera ray: block 0 -> subX, subY ; block 1 -> lens radius, lens angle   (Raytracer.cs:265-273)
+//   stage 1 + i  bounce i:   block 0 -> shine z, shine theta (:53-54) ; block 1 -> lobe pick (:178), diffuse z (:215)
+//                            block 2 -> diffuse theta (:216)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    if (r) {
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+template <typename R>
+__device__ __forceinline__ void uniforms2(uint32_t seed_lo, uint32_t seed_hi, uint32_t pixel, uint32_t sample, uint32_t stage,
+                                          uint32_t block, R& u0, R& u1) {
+  uint32_t r[4];
+  philox4x32_10(pixel, sample, stage, block, seed_lo, seed_hi, r);
+  if constexpr (Num<R>::is_f64) {
+    u0 = (double)((((unsigned long long)r[1] << 32) | r[0]) >> 11) * 0x1.0p-53;
+    u1 = (double)((((unsigned long long)r[3] << 32) | r[2]) >> 11) * 0x1.0p-53;
+  } else {  // the top 24 bits of the same 53-bit draws
+    u0 = (float)(r[1] >> 8) * 0x1.0p-24f;
+    u1 = (float)(r[3] >> 8) * 0x1.0p-24f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Vec4D.CreateHorizontal / CreateHorizon (Vec4D.cs:33-58) with MatrixTransforms.Rotate (MatrixTransforms.cs:25-38)
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ V3<R> create_horizon(const V3<R>& pole, R z, R theta) {
+  V3<R> c = cross3(pole, mk3(R(0), R(0), R(1)));
+  if (c.x == 0 && c.y == 0 && c.z == 0)
+    c = mk3(R(1), R(0), R(0));
+  else
+    c = normalize3(c);
+  R s, co;
+  rsincos(theta, &s, &co);
+  R cosOpp = 1 - co;
+  V3<R> v = (pole * z) + (c * rsqrt_(1 - z * z));
+  const V3<R>& a = pole;
+  R m00 = co + a.x * a.x * cosOpp, m01 = a.x * a.y * cosOpp - a.z * s, m02 = a.x * a.z * cosOpp + a.y * s;
+  R m10 = a.y * a.x * cosOpp + a.z * s, m11 = co + a.y * a.y * cosOpp, m12 = a.y * a.z * cosOpp - a.x * s;
+  R m20 = a.z * a.x * cosOpp - a.y * s, m21 = a.z * a.y * cosOpp + a.x * s, m22 = co + a.z * a.z * cosOpp;
+  return mk3((m00 * v.x + m01 * v.y) + m02 * v.z, (m10 * v.x + m11 * v.y) + m12 * v.z, (m20 * v.x + m21 * v.y) + m22 * v.z);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Primitive tests. A candidate is one entry of the Hit[] a reference DoRayTrace returns (closest first).
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+struct Cand {
+  R t;
+  V3<R> pos;
+  V3<R> normal;  // only filled when WITH_NORMAL
+  bool inside;
+};
+
+// Triangle.RayTraceAVXFaster + GetNormal (Primitives/Triangle.cs:77-146, 209-224)
+template <typename R, bool WITH_NORMAL>
+__device__ __forceinline__ int tri_hits(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
+  const uint32_t slot = ref & REF_SLOT_MASK;
+  const DPrim<R>* pr = sc.prims + slot;
+  V4<R> A = ldg4(&pr->a), B = ldg4(&pr->b), C = ldg4(&pr->c);
+  V3<R> v0 = xyz(A), e1 = xyz(B), e2 = xyz(C);
+  V3<R> off = o - v0;                // :84
+  V3<R> s1 = scross3(off, e1);       // :85
+  V3<R> s2 = scross3(d, e2);         // :86
+  R u = dot3(off, s2);               // :89-97
+  R v = dot3(d, s1);
+  R dist = dot3(e2, s1);
+  R det = dot3(e1, s2);
+  R inv = rrcp(det);                 // :107
+  if (risnan(inv)) inv = 0;          // :108-110
+  u = u * inv;                       // :112
+  v = v * inv;
+  dist = dist * inv;                 // :113
+  bool reject = (u < 0) | (v < 0);   // :116
+  if (ref & REF_MIRROR)
+    reject |= (u > 1) | (v > 1);     // :117-118
+  else
+    reject |= (u + v) > 1;
+  reject |= dist < 0;                // :120
+  if (reject) return 0;
+  bool inside = inv < 0;             // :126
+  out[0].t = dist;
+  out[0].inside = inside;
+  out[0].pos = mk3(rfma(e1.x, u, rfma(e2.x, v, v0.x)), rfma(e1.y, u, rfma(e2.y, v, v0.y)), rfma(e1.z, u, rfma(e2.z, v, v0.z)));  // :130
+  if (WITH_NORMAL) {
+    V3<R> N = mk3(A.w, B.w, C.w);
+    int32_t ax = sc.aux[slot];
+    if (ax >= 0 && (ax & REF_VNORMALS_AUX)) {  // :211-219 (weights and the zero face normal are the reference's)
+      const DXform<R>* xf = sc.xforms + (ax & 0x3FFFFFFF);
+      V3<R> n0 = xyz(ldg4(&xf->r[0])), n1 = xyz(ldg4(&xf->r[1])), n2 = xyz(ldg4(&xf->r[2]));
+      V3<R> nn = normalize3(((n0 * u) + (n1 * v)) + (n2 * (u + v)));
+      if (inside)
+        nn = nn - (N * (2 * (dot3(nn, N)) / dot3(N, N)));
+      out[0].normal = nn;
+    } else {
+      out[0].normal = inside ? (N * R(-1)) : N;  // :221-223
+    }
+  }
+  return 1;
+}
+
+// Sphere.RayTraceAVX (Primitives/Sphere.cs:50-155)
+template <typename R, bool WITH_NORMAL>
+__device__ __forceinline__ int sphere_hits(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
+  const uint32_t slot = ref & REF_SLOT_MASK;
+  V4<R> A = ldg4(&sc.prims[slot].a);
+  V3<R> C = xyz(A);
+  R radius = A.w;
+  const bool xf = ((ref >> REF_KIND_SHIFT) & 3) == DK_XSPHERE;
+  V3<R> oo = o, od = d;
+  V4<R> rows[9];
+  if (xf) {  // :58-76
+    const DXform<R>* x = sc.xforms + sc.aux[slot];
+#pragma unroll
+    for (int i = 0; i < 9; i++) rows[i] = ldg4(&x->r[i]);
+    oo = xf_point(rows, o);
+    od = normalize3(xf_dir(rows, d));
+  }
+  V3<R> off = oo - C;  // :79
+  R t_far, t_close;
+  if constexpr (Num<R>::is_f64) {
+    R b = -2 * dot3(off, od);                     // :80,84
+    R c = dot3(off, off) - radius * radius;       // :81,85 (RadiusSqr = value*value, Sphere.cs:44-45)
+    R radix = rsqrt_((b * b) - (4 * c));          // :86
+    t_far = (b + radix) / 2;                      // :89
+    t_close = (b - radix) / 2;                    // :90
+  } else {
+    // f32: same roots, better-conditioned algebra (perpendicular-distance discriminant, c/q for the small root)
+    R bp = -dot3(off, od);
+    V3<R> l = mk3(rfma(bp, od.x, off.x), rfma(bp, od.y, off.y), rfma(bp, od.z, off.z));
+    R disc = radius * radius - dot3(l, l);
+    R c = dot3(off, off) - radius * radius;
+    R sq = rsqrt_(disc);  // NaN when the ray misses
+    R q = bp + copysignf(sq, bp);
+    R other = c / q;
+    if (bp >= 0) {
+      t_far = q;
+      t_close = other;
+    } else {
+      t_close = q;
+      t_far = other;
+    }
+    if (risnan(sq)) t_far = Num<R>::nan();
+  }
+  if (!(t_far >= 0) && !xf) return 0;  // (for transformed spheres the test applies to the re-measured distances)
+  V3<R> pf = mk3(rfma(t_far, od.x, oo.x), rfma(t_far, od.y, oo.y), rfma(t_far, od.z, oo.z));      // :94
+  V3<R> pc = mk3(rfma(t_close, od.x, oo.x), rfma(t_close, od.y, oo.y), rfma(t_close, od.z, oo.z));  // :97
+  V3<R> nf, nc;
+  if (WITH_NORMAL || xf) {
+    nf = (pf - C) / radius;  // :95
+    nc = (pc - C) / radius;  // :98
+  }
+  if (xf) {  // :100-139
+    pf = xf_point(rows + 3, pf);
+    pc = xf_point(rows + 3, pc);
+    if (WITH_NORMAL) {
+      nf = normalize3(xf_dir(rows + 6, nf));
+      nc = normalize3(xf_dir(rows + 6, nc));
+    }
+    t_far = dot3(d, pf - o);
+    t_close = dot3(d, pc - o);
+    if (!(t_far >= 0)) return 0;  // :145-146
+  }
+  if (WITH_NORMAL) nf = neg3(nf);  // :142
+  if (!(t_close >= 0)) {           // :148-149
+    out[0].t = t_far;
+    out[0].pos = pf;
+    out[0].inside = true;
+    if (WITH_NORMAL) out[0].normal = nf;
+    return 1;
+  }
+  out[0].t = t_close;  // :151-154
+  out[0].pos = pc;
+  out[0].inside = false;
+  out[1].t = t_far;
+  out[1].pos = pf;
+  out[1].inside = true;
+  if (WITH_NORMAL) {
+    out[0].normal = nc;
+    out[1].normal = nf;
+  }
+  return 2;
+}
+
+// Util.NearlyEqual (Util.cs:41-56)
+template <typename R>
+__device__ __forceinline__ bool nearly_equal(R a, R b, R delta) {
+  if (delta == 0) return true;
+  delta = delta < 0 ? -delta : delta;
+  R mx = (risnan(a) || risnan(b)) ? Num<R>::nan() : (a > b ? a : b);  // Math.Max
+  if constexpr (Num<R>::is_f64)
+    return delta <= 4.94065645841247e-317 || delta / mx < 1e-24;  // double.Epsilon * 1e7 ; Util.NearEnough
+  else
+    return delta / mx < 1e-9f;  // f32 stand-in for NearEnough (self-hit rule in float mode)
+}
+
+// Plane.DoRayTrace (Primitives/Plane.cs:36-66)
+template <typename R, bool WITH_NORMAL>
+__device__ __forceinline__ int plane_hits(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
+  const uint32_t slot = ref & REF_SLOT_MASK;
+  V4<R> A = ldg4(&sc.prims[slot].a);
+  V3<R> N = xyz(A);
+  R od = A.w;
+  R ray_dist = dot3(o, N);   // :38
+  R denom = dot3(d, N);      // :39
+  if (nearly_equal(denom, R(0), denom - R(0)) && nearly_equal(od, ray_dist, od - ray_dist)) {  // :41-42
+    out[0].t = 0;
+    out[0].pos = o;
+    out[0].inside = true;
+    if (WITH_NORMAL) out[0].normal = N;
+    return 1;
+  }
+  if (denom == 0) return 0;  // :44-45
+  R dist = (od - ray_dist) / denom;  // :47
+  if (dist >= (Num<R>::is_f64 ? R(-1e-24) : R(0))) {  // :49
+    V3<R> hp = o + (d * dist);  // :51
+    bool inside = dot3(N, d) > 0;  // :56
+    V3<R> dl = hp - o;
+    out[0].t = rsqrt_((dl.x * dl.x + dl.y * dl.y) + dl.z * dl.z);  // :62 (hitPos - ray.Origin).Length
+    out[0].pos = hp;
+    out[0].inside = inside;
+    if (WITH_NORMAL) out[0].normal = inside ? neg3(N) : N;
+    return 1;
+  }
+  return 0;
+}
+
+template <typename R, bool WITH_NORMAL>
+__device__ __forceinline__ int prim_hits(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
+  const int kind = (ref >> REF_KIND_SHIFT) & 3;
+  if (kind == DK_TRI) return tri_hits<R, WITH_NORMAL>(sc, ref, o, d, out);
+  if (kind == DK_PLANE) return plane_hits<R, WITH_NORMAL>(sc, ref, o, d, out);
+  return sphere_hits<R, WITH_NORMAL>(sc, ref, o, d, out);
+}
+
+// The skip hit (previous bounce's Hit) as the trace kernel sees it.
+template <typename R>
+struct Skip {
+  uint32_t slot;  // REF_SLOT_MASK + 1 when there is none
+  bool inside;
+  R t;
+  V3<R> pos, normal;
+};
+
+// Util.RayHitMatches (Util.cs:179-192) for a candidate on the same primitive as the skip hit.
+template <typename R>
+__device__ __noinline__ bool skip_matches(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, int which,
+                                          bool cand_inside, const Cand<R>& cand, const Skip<R>& sk) {
+  if constexpr (!Num<R>::is_f64) {
+    // f32 mode: a flat primitive can only re-hit itself at the ray origin, so the same primitive is always the
+    // self-hit; the positional rule is kept for spheres (their far hit is a legitimate second hit).
+    const int kind = (ref >> REF_KIND_SHIFT) & 3;
+    if (kind == DK_TRI || kind == DK_PLANE) return true;
+  } else {
+    // `a == b` (Hit.cs:44-59): identical primitive, position, distance, normal and inside flag
+    if (cand.pos.x == sk.pos.x && cand.pos.y == sk.pos.y && cand.pos.z == sk.pos.z && cand.t == sk.t &&
+        cand_inside == sk.inside) {
+      Cand<R> full[2];
+      prim_hits<R, true>(sc, ref, o, d, full);
+      const V3<R>& n = full[which].normal;
+      if (n.x == sk.normal.x && n.y == sk.normal.y && n.z == sk.normal.z) return true;
+    }
+  }
+  // Vec4D.NearlyEquals (Vec4D.cs:439-442): squared lengths include W = 1
+  R la = ((cand.pos.x * cand.pos.x + cand.pos.y * cand.pos.y) + cand.pos.z * cand.pos.z) + 1;
+  R lb = ((sk.pos.x * sk.pos.x + sk.pos.y * sk.pos.y) + sk.pos.z * sk.pos.z) + 1;
+  V3<R> dl = cand.pos - sk.pos;
+  R ld = (dl.x * dl.x + dl.y * dl.y) + dl.z * dl.z;
+  if (!nearly_equal(la, lb, ld)) return false;
+  if (dot3(d, sk.normal) > 0) return cand_inside != sk.inside;
+  return cand_inside == sk.inside;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ray / two-box test. f64: AABB.IntersectAVX (Acceleration/AABB.cs:107-142) per child, lane for lane.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ void slab_ref(R lo, R hi, R o, R d, R inv, R& n, R& f) {
+  if (d == 0 && o >= lo && o <= hi) {  // :117-123
+    lo = -Num<R>::inf();
+    hi = Num<R>::inf();
+  }
+  bool sgn = rsignbit(d);  // :126-127
+  R a = sgn ? hi : lo, b = sgn ? lo : hi;
+  n = (a - o) * inv;  // :129-131
+  f = (b - o) * inv;
+}
+
+template <typename R>
+__device__ __forceinline__ bool box_test(R lox, R hix, R loy, R hiy, R loz, R hiz, const V3<R>& o, const V3<R>& d,
+                                         const V3<R>& inv, R& near_out) {
+  if constexpr (Num<R>::is_f64) {
+    R nx, fx, ny, fy, nz, fz;
+    slab_ref(lox, hix, o.x, d.x, inv.x, nx, fx);
+    slab_ref(loy, hiy, o.y, d.y, inv.y, ny, fy);
+    slab_ref(loz, hiz, o.z, d.z, inv.z, nz, fz);
+    // :133-136 with the W lane (-inf, +inf): Max(lower, upper) then MaxScalar(x, swap(x))
+    R nr = sse_max(sse_max(nx, nz), sse_max(ny, -Num<R>::inf()));
+    R fr = sse_min(sse_min(fx, fz), sse_min(fy, Num<R>::inf()));
+    near_out = nr;
+    // :138 miss iff near > far or far < 0 ; BVH.cs:302 then requires far >= 0
+    return !(nr > fr) && (fr >= 0);
+  } else {
+    R t0x = (lox - o.x) * inv.x, t1x = (hix - o.x) * inv.x;
+    R t0y = (loy - o.y) * inv.y, t1y = (hiy - o.y) * inv.y;
+    R t0z = (loz - o.z) * inv.z, t1z = (hiz - o.z) * inv.z;
+    // fminf/fmaxf drop NaN (0 * inf on a slab whose plane contains the origin) == the reference's (-inf,+inf) lane
+    R nr = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+    R fr = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    fr *= 1.0000004f;  // conservative far plane against f32 rounding (Ize 2013)
+    near_out = nr;
+    return (nr <= fr) && (fr >= 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Scene.RayTrace (Raytracing/Scene.cs:65-120): closest hit over the BVH.
+//
+// The reference collects every pierced leaf, stable-sorts by box Near and scans until Near > previous.Far, accepting
+// with a strict `<`; the result is the global closest hit, ties resolved in favour of the smaller (Near, left-first
+// leaf order). This traversal visits nodes front to back with distance pruning and applies exactly that order as a
+// tie key (t, leaf Near, slot), slot being the left-first leaf index, so the answer is independent of visit order.
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+struct Best {
+  R t, near_;
+  uint32_t ref;  // 0xFFFFFFFF = none
+  int which;
+};
+
+template <typename R, bool COUNT>
+__device__ __forceinline__ void test_leaf(const SceneView<R>& sc, uint32_t ref, R leaf_near, const V3<R>& o, const V3<R>& d,
+                                          const Skip<R>& sk, Best<R>& best, uint32_t& n_prims) {
+  if (COUNT) n_prims++;
+  Cand<R> c[2];
+  int n = prim_hits<R, false>(sc, ref, o, d, c);
+  const uint32_t slot = ref & REF_SLOT_MASK;
+  for (int i = 0; i < n; i++) {  // Primitive.RayTrace, Primitives/Primitive.cs:46-75
+    bool inside = c[i].inside ^ ((ref & REF_INVERT) != 0);  // :60-61, Hit.cs:39-42
+    if (inside && !(ref & REF_TWOSIDED)) continue;          // :63-64
+    if (slot == sk.slot && skip_matches<R>(sc, ref, o, d, i, inside, c[i], sk)) continue;  // :66
+    R t = c[i].t;
+    // Scene.cs:85-86 strict `<`; equal distances fall back to the reference's scan order (Near, then leaf order).
+    // A candidate whose distance is NaN or +inf (the reference's det == 0 artefacts) is never taken.
+    bool take = t < best.t;
+    if (!take && t == best.t && best.ref != 0xFFFFFFFFu) {
+      uint32_t bslot = best.ref & REF_SLOT_MASK;
+      take = (leaf_near < best.near_) || (leaf_near == best.near_ && slot < bslot);
+    }
+    if (take) {
+      best.t = t;
+      best.near_ = leaf_near;
+      best.ref = ref;
+      best.which = i;
+    }
+    break;  // :68-70 first acceptable hit of this primitive
+  }
+}
+
+template <typename R, bool COUNT>
+__device__ __forceinline__ void trace_one(const SceneView<R>& sc, const V3<R>& o, const V3<R>& d, const Skip<R>& sk,
+                                          Best<R>& best, uint32_t& n_nodes, uint32_t& n_prims) {
+  V3<R> inv = mk3(rrcp(d.x), rrcp(d.y), rrcp(d.z));
+  if constexpr (Num<R>::is_f64) inv = mk3(R(1) / d.x, R(1) / d.y, R(1) / d.z);  // AABB.cs:129
+  uint32_t stack_node[kTraceStack];
+  R stack_near[kTraceStack];
+  int sp = 0;
+  best.t = Num<R>::inf();
+  best.near_ = 0;
+  best.ref = 0xFFFFFFFFu;
+  best.which = 0;
+  uint32_t node = sc.root;
+  for (;;) {
+    const DNode<R>* np = sc.nodes + node;
+    V4<R> n0 = ldg4(&np->n0), n1 = ldg4(&np->n1), nz = ldg4(&np->nz);
+    uint2 ch = __ldg(reinterpret_cast<const uint2*>(&np->left));
+    if (COUNT) n_nodes++;
+    R nl, nr;
+    bool hl = (ch.x != REF_EMPTY) && box_test<R>(n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, o, d, inv, nl);
+    bool hr = (ch.y != REF_EMPTY) && box_test<R>(n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, o, d, inv, nr);
+    hl = hl && !(nl > best.t);
+    hr = hr && !(nr > best.t);
+    uint32_t c0 = ch.x, c1 = ch.y;
+    if (hl && hr) {
+      if (nr < nl) {
+        uint32_t tc = c0; c0 = c1; c1 = tc;
+        R tn = nl; nl = nr; nr = tn;
+      }
+    } else if (hr) {
+      c0 = c1;
+      nl = nr;
+      hl = true;
+      hr = false;
+    }
+    uint32_t next = 0xFFFFFFFFu;
+    if (hl) {
+      if (c0 & REF_LEAF)
+        test_leaf<R, COUNT>(sc, c0, nl, o, d, sk, best, n_prims);
+      else
+        next = c0;
+    }
+    if (hr && !(nr > best.t)) {
+      if (c1 & REF_LEAF) {
+        test_leaf<R, COUNT>(sc, c1, nr, o, d, sk, best, n_prims);
+      } else if (next == 0xFFFFFFFFu) {
+        next = c1;
+      } else {
+        stack_node[sp] = c1;
+        stack_near[sp] = nr;
+        sp++;
+      }
+    }
+    while (next == 0xFFFFFFFFu) {
+      if (sp == 0) return;
+      sp--;
+      if (!(stack_near[sp] > best.t)) next = stack_node[sp];
+    }
+    node = next;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Cameras and Raytracer.GetCameraRay (Raytracing/Raytracer.cs:262-282, Cameras/FrustumCamera.cs:33-41,
+// Cameras/OrthoCamera.cs:33-38, Vectors/Ray.cs:21-24,53-74)
+// ---------------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ void camera_get_ray(const CameraView<R>& c, R x, R y, V3<R>& o, V3<R>& d) {
+  V3<R> look = mk3(c.look[0], c.look[1], c.look[2]), side = mk3(c.side[0], c.side[1], c.side[2]),
+        up = mk3(c.up[0], c.up[1], c.up[2]), pos = mk3(c.position[0], c.position[1], c.position[2]);
+  if (c.kind == RTC_CAMERA_FRUSTUM) {
+    R off_x = c.tan_fov_x2 * ((x - c.w2) / c.w2);
+    R off_y = c.tan_fov_y2 * ((y - c.h2) / c.h2);
+    V3<R> dir = (look + (side * off_x)) + (up * off_y);
+    o = pos;
+    d = normalize3(dir);
+  } else {
+    o = (pos + (side * ((x - c.w2) * c.h_mult))) + (up * ((y - c.h2) * c.v_mult));
+    d = normalize3(look);
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ void get_camera_ray(const CameraView<R>& c, const ParamsView<R>& par, int x, int y, uint32_t sample,
+                                               V3<R>& o, V3<R>& d) {
+  const uint32_t pixel = (uint32_t)(y * par.width + x);
+  R u0, u1;
+  uniforms2<R>(par.seed_lo, par.seed_hi, pixel, sample, 0, 0, u0, u1);
+  R sub_x = R(x) + u0;
+  R sub_y = R(y) + u1;
+  camera_get_ray(c, sub_x, sub_y, o, d);
+  o = o + (d * c.image_plane);  // Ray.Offset
+  if (c.dof_amount != 0) {
+    V3<R> focus = o + (d * (c.focal_length - c.image_plane));  // Ray.GetPoint
+    R l0, l1;
+    uniforms2<R>(par.seed_lo, par.seed_hi, pixel, sample, 0, 1, l0, l1);
+    R dist = rsqrt_(l0) * c.dof_amount;
+    R angle = l1 * R(3.14159265358979323846) * 2;
+    R sn, cs;
+    rsincos(angle, &sn, &cs);
+    R off_x = cs * dist;
+    R off_y = sn * dist;
+    V3<R> o2, d2;
+    camera_get_ray(c, sub_x + off_x, sub_y + off_y, o2, d2);
+    o2 = o2 + (d2 * c.image_plane);
+    o = o2;
+    d = normalize3(focus - o2);  // PointingTowards -> FromTo
+  }
+}
+
+__device__ __forceinline__ void band_pixel(const Band& b, uint32_t path, int& x, int& y, uint32_t& sample) {
+  uint32_t s_local = path / b.n_pix;
+  uint32_t pix = path - s_local * b.n_pix;
+  uint32_t rw = (uint32_t)(b.x1 - b.x0);
+  uint32_t py = pix / rw;
+  x = b.x0 + (int)(pix - py * rw);
+  y = b.y0 + (int)py;
+  sample = b.first_sample + s_local;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernels
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kStreamThreads = 256;
+constexpr int kTraceThreads = 128;
+
+// raygen: one thread per path of the band. Writes the bounce-0 ray (already re-normalised as GetColor does for
+// i % 3 == 0, Raytracer.cs:74-75), tint = 1 and an empty skip hit.
+template <typename R>
+__global__ void __launch_bounds__(kStreamThreads) k_raygen(CameraView<R> cam, ParamsView<R> par, Band band, PathView<R> pv) {
+  uint32_t path = blockIdx.x * blockDim.x + threadIdx.x;
+  if (path == 0) {
+    pv.ctl->count[0] = band.n_paths;
+    pv.ctl->count[1] = 0;
+    pv.ctl->work_trace = 0;
+  }
+  if (path >= band.n_paths) return;
+  int x, y;
+  uint32_t sample;
+  band_pixel(band, path, x, y, sample);
+  V3<R> o, d;
+  get_camera_ray(cam, par, x, y, sample, o, d);
+  d = normalize3(d);  // Ray.Directional at i == 0
+  st4(&pv.dir[path], d.x, d.y, d.z, R(0));
+  st4(&pv.tint[path], R(1), R(1), R(1), R(0));
+  st4(&pv.hpos[1][path], o.x, o.y, o.z, R(0));
+  R w;
+  set_code(w, HIT_MISS);
+  st4(&pv.hnrm[1][path], R(0), R(0), R(0), w);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kStreamThreads) k_camera_rays(CameraView<R> cam, ParamsView<R> par, int64_t n,
+                                                                 const int32_t* xy, const uint32_t* sample, rtc_ray* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  V3<R> o, d;
+  get_camera_ray(cam, par, xy[2 * i], xy[2 * i + 1], sample[i], o, d);
+  out[i].origin[0] = o.x; out[i].origin[1] = o.y; out[i].origin[2] = o.z;
+  out[i].dir[0] = d.x; out[i].dir[1] = d.y; out[i].dir[2] = d.z;
+}
+
+// trace: persistent warps pull 32 queue entries at a time from a global cursor (dynamic balancing of rays whose
+// traversal lengths differ by orders of magnitude), one ray per lane.
+template <typename R, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads) k_trace(SceneView<R> sc, PathView<R> pv, int q, int prev, int cur,
+                                                          int identity_queue) {
+  const uint32_t count = pv.ctl->count[q];
+  const uint32_t* queue = pv.queue[q];
+  const int lane = threadIdx.x & 31;
+  uint32_t n_nodes = 0, n_prims = 0;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&pv.ctl->work_trace, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= count) break;
+    uint32_t idx = base + lane;
+    if (idx < count) {
+      uint32_t path = identity_queue ? idx : queue[idx];
+      V4<R> dv = ld4(&pv.dir[path]);
+      V4<R> op = ld4(&pv.hpos[prev][path]);
+      V4<R> sn = ld4(&pv.hnrm[prev][path]);
+      V3<R> o = xyz(op), d = xyz(dv);
+      Skip<R> sk;
+      uint32_t code = code_of(sn.w);
+      sk.slot = (code == HIT_MISS) ? (REF_SLOT_MASK + 1) : (code & REF_SLOT_MASK);
+      sk.inside = (code & HIT_INSIDE) != 0;
+      sk.t = op.w;
+      sk.normal = xyz(sn);
+      sk.pos = o;
+      if (pv.skip_pos) sk.pos = xyz(ld4(&pv.skip_pos[path]));
+      Best<R> best;
+      trace_one<R, COUNT>(sc, o, d, sk, best, n_nodes, n_prims);
+      if (best.ref == 0xFFFFFFFFu) {
+        R w;
+        set_code(w, HIT_MISS);
+        st4(&pv.hpos[cur][path], R(0), R(0), R(0), R(0));
+        st4(&pv.hnrm[cur][path], R(0), R(0), R(0), w);
+      } else {
+        Cand<R> c[2];
+        prim_hits<R, true>(sc, best.ref, o, d, c);
+        const Cand<R>& h = c[best.which];
+        bool inside = h.inside ^ ((best.ref & REF_INVERT) != 0);
+        R w;
+        set_code(w, (best.ref & REF_SLOT_MASK) | (inside ? HIT_INSIDE : 0u));
+        st4(&pv.hpos[cur][path], h.pos.x, h.pos.y, h.pos.z, h.t);
+        st4(&pv.hnrm[cur][path], h.normal.x, h.normal.y, h.normal.z, w);
+      }
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&pv.ctl->nodes_visited, (unsigned long long)n_nodes);
+    atomicAdd(&pv.ctl->prims_tested, (unsigned long long)n_prims);
+  }
+}
+
+// DoubleColor.Luminance (DoubleColor.cs:76-81)
+template <typename R>
+__device__ __forceinline__ R luminance(R r, R g, R b) { return (R(0.299) * r + R(0.587) * g) + R(0.114) * b; }
+
+// shade: one bounce of Raytracer.GetColor (Raytracing/Raytracer.cs:71-245) for every live path: terminal tests,
+// RandomShine, Fresnel / total internal reflection, lobe roulette, next ray, tint. Terminated paths write their
+// radiance and set Q_DEAD on their queue entry; the others overwrite dir/tint in place.
+template <typename R>
+__global__ void __launch_bounds__(kStreamThreads) k_shade(SceneView<R> sc, ParamsView<R> par, Band band, PathView<R> pv, int q,
+                                                           int cur, int bounce, int identity_queue) {
+  const uint32_t count = pv.ctl->count[q];
+  uint32_t* queue = pv.queue[q];
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+    const uint32_t path = identity_queue ? idx : queue[idx];
+    V4<R> hp = ld4(&pv.hpos[cur][path]);
+    V4<R> hn = ld4(&pv.hnrm[cur][path]);
+    const uint32_t code = code_of(hn.w);
+    bool done = false;
+    R out_r = 0, out_g = 0, out_b = 0;
+    int dbg = 0;  // BounceType.Skipped
+    R dbg_f = Num<R>::nan();
+    if (code == HIT_MISS) {  // :81-91
+      dbg = 8;
+      if (bounce == 0) {
+        out_r = out_g = out_b = R(-1);  // DoubleColor.Placeholder
+      } else {
+        out_r = par.ambient[0];
+        out_g = par.ambient[1];
+        out_b = par.ambient[2];
+      }
+      done = true;
+    } else {
+      const uint32_t slot = code & REF_SLOT_MASK;
+      const bool hit_inside = (code & HIT_INSIDE) != 0;
+      const DMat<R>* mp = sc.mats + slot;
+      V4<R> m_emis = ldg4(&mp->emis_ior), m_diff = ldg4(&mp->diff_shin), m_spec = ldg4(&mp->spec), m_refr = ldg4(&mp->refr);
+      V4<R> tv = ld4(&pv.tint[path]);
+      if (par.debug_geom) {  // :93-98
+        dbg = 9;
+        out_r = (m_spec.x + m_diff.x) + m_emis.x;
+        out_g = (m_spec.y + m_diff.y) + m_emis.y;
+        out_b = (m_spec.z + m_diff.z) + m_emis.z;
+        done = true;
+      } else if (bounce >= par.recursion) {  // :100-104
+        dbg = 7;
+        out_r = tv.x * m_emis.x;
+        out_g = tv.y * m_emis.y;
+        out_b = tv.z * m_emis.z;
+        done = true;
+      } else {
+        int x, y;
+        uint32_t sample;
+        band_pixel(band, path, x, y, sample);
+        const uint32_t pixel = (uint32_t)(y * par.width + x);
+        const uint32_t stage = 1u + (uint32_t)bounce;
+        V4<R> dv = ld4(&pv.dir[path]);
+        V3<R> d = xyz(dv), normal = xyz(hn);
+        const R shininess = m_diff.w, ior = m_emis.w;
+        R u1, u2;
+        uniforms2<R>(par.seed_lo, par.seed_hi, pixel, sample, stage, 0, u1, u2);
+        // RandomShine, :51-56
+        R zs = (shininess == Num<R>::inf()) ? R(1) : rpow(u1, 1 / shininess);
+        R theta_s = u2 * R(3.14159265358979323846) * 2;
+        V3<R> rough = create_horizon(normal, zs, theta_s);  // :108
+        R diff_l = luminance(m_diff.x, m_diff.y, m_diff.z), spec_l = luminance(m_spec.x, m_spec.y, m_spec.z),
+          refr_l = luminance(m_refr.x, m_refr.y, m_refr.z), emis_l = luminance(m_emis.x, m_emis.y, m_emis.z);  // :110-113
+        R cosv = -dot3(rough, d);  // :115
+        R cos_out = 0, ior_ratio = 0;
+        if (((refr_l > 0) | (spec_l > 0)) && ior != 0 && cosv >= 0) {  // :120
+          R ior_in, ior_out;
+          if (hit_inside) {
+            ior_in = ior;
+            ior_out = par.air_ior;
+          } else {
+            ior_in = par.air_ior;
+            ior_out = ior;
+          }
+          ior_ratio = ior_in / ior_out;                              // :136
+          R sin_out = ior_ratio * rsqrt_(1 - (cosv * cosv));         // :137
+          if (sin_out >= 1) {                                        // :140-145
+            refr_l = 0;
+            dbg_f = 1;
+          } else {
+            cos_out = rsqrt_(1 - (sin_out * sin_out));               // :148
+            R rs = ((ior_out * cosv) - (ior_in * cos_out)) / ((ior_out * cosv) + (ior_in * cos_out));  // :149
+            R rp = ((ior_in * cosv) - (ior_out * cos_out)) / ((ior_in * cosv) + (ior_out * cos_out));  // :150
+            R ratio = ((rs * rs) + (rp * rp)) / 2;                   // :151
+            spec_l *= ratio;
+            refr_l *= 1 - ratio;
+            dbg_f = ratio;
+          }
+        } else {
+          refr_l = 0;  // :158-161
+        }
+        R total_l = ((diff_l + spec_l) + refr_l) + emis_l;  // :163
+        bool have_out = false;
+        V3<R> out_dir = mk3(R(0), R(0), R(0));
+        R nt_r = 0, nt_g = 0, nt_b = 0;
+        if (total_l <= 0) {  // :165-169
+          dbg = 6;
+        } else {
+          R u3, u4;
+          uniforms2<R>(par.seed_lo, par.seed_hi, pixel, sample, stage, 1, u3, u4);
+          R ray_rand = u3 * total_l;  // :178
+          if (refr_l != 0 && (ray_rand -= refr_l) <= 0) {  // :181-193
+            dbg = 4;
+            out_dir = (rough * -cos_out) + ((d + (rough * cosv)) * ior_ratio);
+            have_out = true;
+            if (hit_inside) {
+              nt_r = nt_g = nt_b = 1;
+            } else {
+              nt_r = m_refr.x; nt_g = m_refr.y; nt_b = m_refr.z;
+            }
+          } else if (spec_l != 0 && (ray_rand -= spec_l) <= 0) {  // :194-209
+            dbg = 3;
+            V3<R> od = d + (rough * (cosv * 2));  // Reflection, :58-61
+            if (dot3(od, normal) > 0) {
+              dbg = 2;
+              out_dir = od;
+              have_out = true;
+              nt_r = m_spec.x; nt_g = m_spec.y; nt_b = m_spec.z;
+            }
+          } else if (diff_l != 0 && (ray_rand -= diff_l) <= 0) {  // :210-219
+            dbg = 1;
+            R u5, u6;
+            uniforms2<R>(par.seed_lo, par.seed_hi, pixel, sample, stage, 2, u5, u6);
+            R z = (2 * racos(u4)) / R(3.14159265358979323846);
+            R theta = u5 * R(3.14159265358979323846) * 2;
+            out_dir = create_horizon(normal, z, theta);
+            have_out = true;
+            nt_r = m_diff.x; nt_g = m_diff.y; nt_b = m_diff.z;
+          } else {
+            dbg = 5;  // :220-229 emission picked
+          }
+          // :231-232 `outRay == Ray.Zero`
+          if (have_out && hp.x == 0 && hp.y == 0 && hp.z == 0 && out_dir.x == 0 && out_dir.y == 0 && out_dir.z == 0)
+            have_out = false;
+        }
+        if (have_out) {
+          R m = risnan(total_l) ? total_l : (total_l > 1 ? total_l : R(1));  // Math.Max(totalLum, 1), :238
+          R tr = tv.x * (nt_r * m), tg = tv.y * (nt_g * m), tb = tv.z * (nt_b * m);  // :238-240
+          if ((bounce + 1) % 3 == 0) out_dir = normalize3(out_dir);  // :74-75 of the next iteration
+          st4(&pv.dir[path], out_dir.x, out_dir.y, out_dir.z, R(0));
+          st4(&pv.tint[path], tr, tg, tb, R(0));
+        } else {
+          out_r = tv.x * m_emis.x;  // :245
+          out_g = tv.y * m_emis.y;
+          out_b = tv.z * m_emis.z;
+          done = true;
+        }
+      }
+    }
+    if (pv.dbg_type) {
+      pv.dbg_type[path] = dbg;
+      pv.dbg_fresnel[path] = dbg_f;
+    }
+    if (done) {
+      st4(&pv.radiance[path], out_r, out_g, out_b, R(0));
+      queue[idx] = path | Q_DEAD;
+    } else if (identity_queue) {
+      queue[idx] = path;
+    }
+  }
+}
+
+// compact: warp-aggregated stream compaction of the queue (one atomicAdd per warp). Also folds the bookkeeping of
+// the bounce: ray counter, reset of the trace cursor, zeroing of the queue length just consumed.
+static __global__ void __launch_bounds__(kStreamThreads) k_compact(const uint32_t* __restrict__ qin, uint32_t* __restrict__ qout,
+                                                             Control* ctl, int q) {
+  const uint32_t count = ctl->count[q];
+  const int lane = threadIdx.x & 31;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (count + stride - 1) / stride;
+  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t r = 0; r < rounds; r++, idx += stride) {
+    uint32_t e = idx < count ? qin[idx] : Q_DEAD;
+    bool alive = !(e & Q_DEAD);
+    uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
+    if (mask) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&ctl->count[q ^ 1], (uint32_t)__popc(mask));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (alive) qout[base + __popc(mask & ((1u << lane) - 1))] = e;
+    }
+  }
+}
+
+static __global__ void k_end_bounce(Control* ctl, int q) {
+  ctl->rays += ctl->count[q];
+  ctl->count[q] = 0;
+  ctl->work_trace = 0;
+}
+
+// accumulate: FullRaytracer's drain loop (FullRaytracer.cs:326-339) + SampleSet.AddSample/AddMiss (SampleSet.cs:32-44),
+// one thread per pixel of the band, samples added in ascending order (deterministic, no atomics).
+template <typename R>
+__global__ void __launch_bounds__(kStreamThreads) k_accumulate(ParamsView<R> par, Band band, PathView<R> pv, double* rgb_sum,
+                                                                uint32_t* samples, uint32_t* misses) {
+  uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= band.n_pix) return;
+  uint32_t rw = (uint32_t)(band.x1 - band.x0);
+  uint32_t py = pix / rw;
+  size_t g = (size_t)(band.y0 + (int)py) * par.width + (band.x0 + (int)(pix - py * rw));
+  double r = rgb_sum[g * 3 + 0], gg = rgb_sum[g * 3 + 1], b = rgb_sum[g * 3 + 2];
+  uint32_t ns = samples[g], nm = misses[g];
+  for (uint32_t s = 0; s < band.n_samples; s++) {
+    V4<R> c = ld4(&pv.radiance[(size_t)s * band.n_pix + pix]);
+    if (c.x == R(-1) && c.y == R(-1) && c.z == R(-1)) {  // == DoubleColor.Placeholder -> AddMiss
+      nm++;
+    } else {
+      r += (double)c.x;
+      gg += (double)c.y;
+      b += (double)c.z;
+      ns++;
+    }
+  }
+  rgb_sum[g * 3 + 0] = r;
+  rgb_sum[g * 3 + 1] = gg;
+  rgb_sum[g * 3 + 2] = b;
+  samples[g] = ns;
+  misses[g] = nm;
+}
+
+// ---- rtc_trace_closest plumbing --------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(kStreamThreads) k_import_rays(SceneView<R> sc, int64_t n, const rtc_ray* rays,
+                                                                 const rtc_hit* skip, const int32_t* id_to_slot,
+                                                                 PathView<R> pv, int prev) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    pv.ctl->count[0] = (uint32_t)n;
+    pv.ctl->count[1] = 0;
+    pv.ctl->work_trace = 0;
+  }
+  if (i >= n) return;
+  const rtc_ray& r = rays[i];
+  st4(&pv.dir[i], (R)r.dir[0], (R)r.dir[1], (R)r.dir[2], R(0));
+  R t = 0, w;
+  R nx = 0, ny = 0, nz = 0, px = 0, py = 0, pz = 0;
+  uint32_t code = HIT_MISS;
+  if (skip && skip[i].prim >= 0 && skip[i].prim < sc.n_prims) {
+    const rtc_hit& s = skip[i];
+    code = (uint32_t)id_to_slot[s.prim] | (s.inside ? HIT_INSIDE : 0u);
+    t = (R)s.t;
+    nx = (R)s.normal[0]; ny = (R)s.normal[1]; nz = (R)s.normal[2];
+    px = (R)s.position[0]; py = (R)s.position[1]; pz = (R)s.position[2];
+  }
+  set_code(w, code);
+  st4(&pv.hpos[prev][i], (R)r.origin[0], (R)r.origin[1], (R)r.origin[2], t);
+  st4(&pv.hnrm[prev][i], nx, ny, nz, w);
+  st4(&pv.skip_pos[i], px, py, pz, R(0));
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kStreamThreads) k_export_hits(SceneView<R> sc, int64_t n, PathView<R> pv, int cur, rtc_hit* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  V4<R> hp = ld4(&pv.hpos[cur][i]);
+  V4<R> hn = ld4(&pv.hnrm[cur][i]);
+  uint32_t code = code_of(hn.w);
+  rtc_hit h;
+  if (code == HIT_MISS) {
+    h.prim = -1;
+    h.inside = 0;
+    h.t = 0;
+    h.position[0] = h.position[1] = h.position[2] = 0;
+    h.normal[0] = h.normal[1] = h.normal[2] = 0;
+  } else {
+    h.prim = sc.prim_id[code & REF_SLOT_MASK];
+    h.inside = (code & HIT_INSIDE) ? 1 : 0;
+    h.t = (double)hp.w;
+    h.position[0] = (double)hp.x; h.position[1] = (double)hp.y; h.position[2] = (double)hp.z;
+    h.normal[0] = (double)hn.x; h.normal[1] = (double)hn.y; h.normal[2] = (double)hn.z;
+  }
+  out[i] = h;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kStreamThreads) k_export_radiance(Band band, ParamsView<R> par, PathView<R> pv, double* out_rgb) {
+  uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= band.n_pix) return;
+  uint32_t rw = (uint32_t)(band.x1 - band.x0);
+  uint32_t py = pix / rw;
+  size_t g = (size_t)(band.y0 + (int)py) * par.width + (band.x0 + (int)(pix - py * rw));
+  V4<R> c = ld4(&pv.radiance[pix]);
+  out_rgb[g * 3 + 0] = (double)c.x;
+  out_rgb[g * 3 + 1] = (double)c.y;
+  out_rgb[g * 3 + 2] = (double)c.z;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Launchers
+// ---------------------------------------------------------------------------------------------------------
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+template <typename R>
+int Kernels<R>::trace_blocks_per_sm() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<R, false>, kTraceThreads, 0);
+  return nb > 0 ? nb : 1;
+}
+
+template <typename R>
+cudaError_t Kernels<R>::raygen(const LaunchCfg& cfg, const CameraView<R>& cam, const ParamsView<R>& par, const Band& band,
+                               const PathView<R>& pv) {
+  k_raygen<R><<<div_up(band.n_paths, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(cam, par, band, pv);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Kernels<R>::camera_rays(const LaunchCfg& cfg, const CameraView<R>& cam, const ParamsView<R>& par, int64_t n,
+                                    const int32_t* xy, const uint32_t* sample, rtc_ray* out) {
+  if (n == 0) return cudaSuccess;
+  k_camera_rays<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(cam, par, n, xy, sample, out);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, int prev, int cur,
+                              bool identity_queue) {
+  static int per_sm = trace_blocks_per_sm();
+  int grid = cfg.sm_count * per_sm;
+  if (cfg.counters)
+    k_trace<R, true><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+  else
+    k_trace<R, false><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Kernels<R>::shade(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,
+                              const PathView<R>& pv, int q, int cur, int bounce, bool identity_queue) {
+  int grid = cfg.sm_count * 8;
+  k_shade<R><<<grid, kStreamThreads, 0, cfg.stream>>>(sc, par, band, pv, q, cur, bounce, identity_queue ? 1 : 0);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Kernels<R>::compact(const LaunchCfg& cfg, const PathView<R>& pv, int q, bool) {
+  int grid = cfg.sm_count * 8;
+  k_compact<<<grid, kStreamThreads, 0, cfg.stream>>>(pv.queue[q], pv.queue[q ^ 1], pv.ctl, q);
+  k_end_bounce<<<1, 1, 0, cfg.stream>>>(pv.ctl, q);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Kernels<R>::accumulate(const LaunchCfg& cfg, const ParamsView<R>& par, const Band& band, const PathView<R>& pv,
+                                   double* rgb_sum, uint32_t* samples, uint32_t* misses) {
+  k_accumulate<R><<<div_up(band.n_pix, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(par, band, pv, rgb_sum, samples, misses);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Kernels<R>::import_rays(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const rtc_ray* rays,
+                                    const rtc_hit* skip, const int32_t* id_to_slot, const PathView<R>& pv, int prev) {
+  k_import_rays<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, n, rays, skip, id_to_slot, pv, prev);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Kernels<R>::export_hits(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const PathView<R>& pv, int cur,
+                                    rtc_hit* out) {
+  k_export_hits<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, n, pv, cur, out);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Kernels<R>::export_radiance(const LaunchCfg& cfg, const Band& band, const ParamsView<R>& par, const PathView<R>& pv,
+                                        double* out_rgb) {
+  k_export_radiance<R><<<div_up(band.n_pix, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(band, par, pv, out_rgb);
+  return cudaGetLastError();
+}
+
+}  // namespace rtc

@@ -1,0 +1,164 @@
+// rtc_internal.h — device data layout and the launcher interface shared by the C-ABI host code (rtc_api.cu)
+// and the two kernel translation units (kernels_f32.cu built with -fmad=true, kernels_f64.cu with -fmad=false).
+//
+// HBM layout (R = float in RTC_F32 mode, double in RTC_F64 mode; V4<R> is one 16-byte / 32-byte vector load):
+//   DNode<R>  4 x V4: both children's boxes + two child references. 64 B (f32): two nodes per 128-B line.
+//   DPrim<R>  3 x V4 per primitive, stored in left-first DFS leaf order so slot == leaf order (tie-break key):
+//               triangle  a=(v0.xyz,N.x) b=(e1.xyz,N.y) c=(e2.xyz,N.z)      (Triangle.cs:22-29)
+//               sphere    a=(center.xyz,radius)                              (Sphere.cs:11-14)
+//               plane     a=(normal.xyz,originDistance)                      (Plane.cs:13-14)
+//   DXform<R> 9 x V4 for transformed spheres (rows 0-2 of MatrixToWorld, MatrixToObject, MatrixToNormal) or
+//             vertex-normal triangles (n0,n1,n2 in rows 0-2).
+//   DMat<R>   4 x V4: (emission, ior) (diffuse, shininess) (specular, 0) (refraction, 0)  (Primitive.cs:16-129)
+//   path pool: SoA of V4<R> per path: dir, tint, 2 x (hit position|t, hit normal|code) ping-pong, radiance.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtcore_b200.h"
+
+namespace rtc {
+
+template <typename R>
+struct alignas(sizeof(R) * 4) V4 {
+  R x, y, z, w;
+};
+
+// child reference encoding
+constexpr uint32_t REF_LEAF = 0x80000000u;
+constexpr uint32_t REF_EMPTY = 0x7FFFFFFFu;  // inner-node slot that is never hit (padding child of a 1-leaf tree)
+constexpr int REF_KIND_SHIFT = 29;           // 2 bits: DK_*
+constexpr uint32_t REF_MIRROR = 1u << 28;
+constexpr uint32_t REF_TWOSIDED = 1u << 27;
+constexpr uint32_t REF_INVERT = 1u << 26;
+constexpr uint32_t REF_SLOT_MASK = (1u << 26) - 1;
+enum { DK_TRI = 0, DK_SPHERE = 1, DK_XSPHERE = 2, DK_PLANE = 3 };
+constexpr uint32_t REF_VNORMALS_AUX = 0x40000000u;  // flag kept in aux[] for vertex-normal triangles
+
+// hit code stored in the w lane of the hit-normal vector
+constexpr uint32_t HIT_MISS = 0xFFFFFFFFu;
+constexpr uint32_t HIT_INSIDE = 1u << 30;
+
+constexpr uint32_t Q_DEAD = 0x80000000u;  // queue entry flag written by shade for terminated paths
+
+constexpr int kTraceStack = 128;
+
+template <typename R>
+struct alignas(sizeof(R) * 4) DNode {
+  V4<R> n0;  // left child:  min.x max.x min.y max.y
+  V4<R> n1;  // right child: min.x max.x min.y max.y
+  V4<R> nz;  // left min.z max.z, right min.z max.z
+  uint32_t left, right, pad0, pad1;
+};
+
+template <typename R>
+struct DPrim {
+  V4<R> a, b, c;
+};
+
+template <typename R>
+struct DXform {
+  V4<R> r[9];
+};
+
+template <typename R>
+struct DMat {
+  V4<R> emis_ior, diff_shin, spec, refr;
+};
+
+template <typename R>
+struct SceneView {
+  const DNode<R>* nodes;
+  const DPrim<R>* prims;
+  const DXform<R>* xforms;
+  const DMat<R>* mats;
+  const int32_t* aux;      // per slot: xform row (low 30 bits) | REF_VNORMALS_AUX, or -1
+  const int32_t* prim_id;  // per slot: Primitive.ID
+  const uint32_t* prim_ref;  // per slot: the leaf reference (kind + flags + slot)
+  uint32_t root;           // index of the root inner node
+  int32_t n_prims;
+};
+
+template <typename R>
+struct CameraView {
+  int32_t kind;
+  R position[3], look[3], side[3], up[3];
+  R w2, h2, tan_fov_x2, tan_fov_y2, h_mult, v_mult, image_plane, dof_amount, focal_length;
+};
+
+template <typename R>
+struct ParamsView {
+  int32_t width, height, recursion, debug_geom;
+  R ambient[3];
+  R air_ior;
+  uint32_t seed_lo, seed_hi;
+};
+
+// The wavefront band a launch works on: pixels [x0,x1) x [y0,y1), samples first_sample .. +n_samples-1.
+// path id = s_local * n_pix + pix_local ; pix_local = (y-y0)*(x1-x0) + (x-x0)
+struct Band {
+  int32_t x0, y0, x1, y1;
+  uint32_t first_sample, n_samples;
+  uint32_t n_pix, n_paths;
+};
+
+struct Control {            // device-resident launch control block
+  uint32_t count[2];        // live queue lengths (ping-pong)
+  uint32_t work_trace;      // dynamic work cursor of the persistent trace kernel
+  uint32_t pad;
+  unsigned long long rays;  // closest-hit queries issued (sum of queue lengths over bounces)
+  unsigned long long nodes_visited, prims_tested;  // RTC_OPT_COUNTERS
+};
+
+template <typename R>
+struct PathView {
+  V4<R>* dir;       // xyz = direction
+  V4<R>* tint;      // rgb
+  V4<R>* hpos[2];   // xyz = hit position (or ray origin for bounce 0), w = Hit.Distance
+  V4<R>* hnrm[2];   // xyz = hit normal, w = hit code bits
+  V4<R>* radiance;  // rgb of finished paths ((-1,-1,-1) = miss)
+  V4<R>* skip_pos;  // optional (rtc_trace_closest only): explicit skip-hit position; nullptr = ray origin
+  uint32_t* queue[2];
+  Control* ctl;
+  int32_t* dbg_type;  // optional per-path BounceType (rtc_debug_trace)
+  R* dbg_fresnel;     // optional per-path FresnelRatio
+};
+
+struct LaunchCfg {
+  cudaStream_t stream;
+  int sm_count;
+  bool counters;
+};
+
+// Launchers, one set per arithmetic mode. All are asynchronous on cfg.stream.
+template <typename R>
+struct Kernels {
+  static cudaError_t raygen(const LaunchCfg& cfg, const CameraView<R>& cam, const ParamsView<R>& par, const Band& band,
+                            const PathView<R>& pv);
+  // explicit (x,y,sample) list -> rtc_ray (f64) ; used by rtc_camera_rays
+  static cudaError_t camera_rays(const LaunchCfg& cfg, const CameraView<R>& cam, const ParamsView<R>& par, int64_t n,
+                                 const int32_t* xy, const uint32_t* sample, rtc_ray* out);
+  // bounce `bounce`: reads queue[q] (nullptr semantics: identity when bounce == 0), hit buffer `prev`, writes `cur`
+  static cudaError_t trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, int prev, int cur,
+                           bool identity_queue);
+  static cudaError_t shade(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,
+                           const PathView<R>& pv, int q, int cur, int bounce, bool identity_queue);
+  static cudaError_t compact(const LaunchCfg& cfg, const PathView<R>& pv, int q, bool identity_queue);
+  static cudaError_t accumulate(const LaunchCfg& cfg, const ParamsView<R>& par, const Band& band, const PathView<R>& pv,
+                                double* rgb_sum, uint32_t* samples, uint32_t* misses);
+  // rtc_trace_closest plumbing
+  static cudaError_t import_rays(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const rtc_ray* rays,
+                                 const rtc_hit* skip, const int32_t* id_to_slot, const PathView<R>& pv, int prev);
+  static cudaError_t export_hits(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const PathView<R>& pv, int cur,
+                                 rtc_hit* out);
+  static cudaError_t export_radiance(const LaunchCfg& cfg, const Band& band, const ParamsView<R>& par,
+                                     const PathView<R>& pv, double* out_rgb);
+  static int trace_blocks_per_sm();
+};
+
+// mode-independent
+cudaError_t launch_tonemap(cudaStream_t s, int32_t n, const double* rgb_sum, const uint32_t* samples,
+                           const uint32_t* misses, double exposure, double br, double bg, double bb, double ba,
+                           uint32_t* argb);
+
+}  // namespace rtc
