@@ -176,6 +176,10 @@ void rtc_destroy(rtc_ctx* ctx);
 /* Text of the last error on this context (ctx == NULL: last error of a failed rtc_create on this thread). */
 const char* rtc_last_error(rtc_ctx* ctx);
 int rtc_set_option(rtc_ctx* ctx, int option, int64_t value);
+/* Run all of this context's work on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores the
+ * context's own stream). Lets a host that already owns a stream (and times it with its own events) order the
+ * render passes and the per-frame collective with its other work. */
+int rtc_set_stream(rtc_ctx* ctx, void* cuda_stream);
 
 /* ---- scene hand-over: what Scene.Prepare + FullRaytracer.Start set up (FullRaytracer.cs:253-269) ----- */
 /* Scene.Primitives + materials (Scene.cs:28,160). Invalidates any BVH previously set. */

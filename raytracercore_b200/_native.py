@@ -82,6 +82,7 @@ SIGNATURES = {
     "rtc_destroy": (None, [_P]),
     "rtc_last_error": (C.c_char_p, [_P]),
     "rtc_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
+    "rtc_set_stream": (C.c_int, [_P, _P]),
     "rtc_upload_scene": (C.c_int, [_P, C.POINTER(SceneDesc)]),
     "rtc_upload_bvh": (C.c_int, [_P, C.c_int32, C.POINTER(BvhNode), C.c_int32]),
     "rtc_build_bvh": (C.c_int, [_P]),

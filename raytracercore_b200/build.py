@@ -47,6 +47,10 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers += [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")]
     headers += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
+    all_src = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu")]
+    all_src += [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".cpp")]
+    if not force and not _newer(LIB, all_src + headers):
+        return LIB  # up to date (also the case on the GPU box, where the prebuilt library travels with the snapshot)
     objs = []
     units = [
         ("kernels_f32.cu", NVCC_COMMON),

@@ -72,7 +72,8 @@ struct rtc_ctx {
   int device = 0;
   int precision = RTC_F32;
   std::string err;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream all work is issued on
+  cudaStream_t own_stream = nullptr;  // created by rtc_create
   int sm_count = 148;
 
   // host copy of the scene as handed over (f64)
@@ -323,7 +324,7 @@ int build_device_scene(rtc_ctx* ctx) {
     }
   }
   if ((int32_t)slot_prim.size() != n) return fail(ctx, RTC_ERR_INVALID, "BVH does not reference every primitive exactly once");
-  if (max_depth > kTraceStack) return fail(ctx, RTC_ERR_UNSUPPORTED, "BVH depth " + std::to_string(max_depth) + " exceeds the traversal stack (" + std::to_string(kTraceStack) + ")");
+  if (max_depth + 2 > kTraceStack) return fail(ctx, RTC_ERR_UNSUPPORTED, "BVH depth " + std::to_string(max_depth) + " exceeds the traversal stack (" + std::to_string(kTraceStack) + ")");
   ctx->bvh_depth = max_depth;
 
   auto leaf_ref = [&](int32_t node) -> uint32_t {
@@ -670,7 +671,17 @@ int rtc_create(int device, int precision, rtc_ctx** out) {
     delete ctx;
     return RTC_ERR_CUDA;
   }
+  ctx->own_stream = ctx->stream;
   *out = ctx;
+  return RTC_OK;
+}
+
+int rtc_set_stream(rtc_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return RTC_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  drain_timing(ctx);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return RTC_OK;
 }
 
@@ -690,7 +701,7 @@ void rtc_destroy(rtc_ctx* ctx) {
   free_dev_t(ctx->d_rgb);
   free_dev_t(ctx->d_samples);
   free_dev_t(ctx->d_misses);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 

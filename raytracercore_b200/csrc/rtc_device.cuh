@@ -386,41 +386,47 @@ __device__ __forceinline__ int prim_hits(const SceneView<R>& sc, uint32_t ref, c
   return sphere_hits<R, WITH_NORMAL>(sc, ref, o, d, out);
 }
 
-// The skip hit (previous bounce's Hit) as the trace kernel sees it.
+// The skip hit (previous bounce's Hit) as the trace kernel sees it: primitive slot and inside flag live in
+// registers, the rest (position, distance, normal) stays in the path's previous-hit record and is only read on
+// the rare occasion a candidate lies on the same primitive.
 template <typename R>
 struct Skip {
   uint32_t slot;  // REF_SLOT_MASK + 1 when there is none
   bool inside;
-  R t;
-  V3<R> pos, normal;
+  const V4<R>* hpos;  // xyz = skip position (= ray origin in the render loop), w = skip Hit.Distance
+  const V4<R>* hnrm;  // xyz = skip normal
+  const V4<R>* spos;  // explicit skip position (rtc_trace_closest) or nullptr
 };
 
 // Util.RayHitMatches (Util.cs:179-192) for a candidate on the same primitive as the skip hit.
 template <typename R>
 __device__ __noinline__ bool skip_matches(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, int which,
-                                          bool cand_inside, const Cand<R>& cand, const Skip<R>& sk) {
+                                          bool cand_inside, R cand_t, const V3<R>& cand_pos, const Skip<R>& sk) {
   if constexpr (!Num<R>::is_f64) {
     // f32 mode: a flat primitive can only re-hit itself at the ray origin, so the same primitive is always the
     // self-hit; the positional rule is kept for spheres (their far hit is a legitimate second hit).
     const int kind = (ref >> REF_KIND_SHIFT) & 3;
     if (kind == DK_TRI || kind == DK_PLANE) return true;
-  } else {
+  }
+  V4<R> hp = ld4(sk.hpos), hn = ld4(sk.hnrm);
+  V3<R> spos = sk.spos ? xyz(ld4(sk.spos)) : xyz(hp);
+  V3<R> snrm = xyz(hn);
+  if constexpr (Num<R>::is_f64) {
     // `a == b` (Hit.cs:44-59): identical primitive, position, distance, normal and inside flag
-    if (cand.pos.x == sk.pos.x && cand.pos.y == sk.pos.y && cand.pos.z == sk.pos.z && cand.t == sk.t &&
-        cand_inside == sk.inside) {
+    if (cand_pos.x == spos.x && cand_pos.y == spos.y && cand_pos.z == spos.z && cand_t == hp.w && cand_inside == sk.inside) {
       Cand<R> full[2];
       prim_hits<R, true>(sc, ref, o, d, full);
       const V3<R>& n = full[which].normal;
-      if (n.x == sk.normal.x && n.y == sk.normal.y && n.z == sk.normal.z) return true;
+      if (n.x == snrm.x && n.y == snrm.y && n.z == snrm.z) return true;
     }
   }
   // Vec4D.NearlyEquals (Vec4D.cs:439-442): squared lengths include W = 1
-  R la = ((cand.pos.x * cand.pos.x + cand.pos.y * cand.pos.y) + cand.pos.z * cand.pos.z) + 1;
-  R lb = ((sk.pos.x * sk.pos.x + sk.pos.y * sk.pos.y) + sk.pos.z * sk.pos.z) + 1;
-  V3<R> dl = cand.pos - sk.pos;
+  R la = ((cand_pos.x * cand_pos.x + cand_pos.y * cand_pos.y) + cand_pos.z * cand_pos.z) + 1;
+  R lb = ((spos.x * spos.x + spos.y * spos.y) + spos.z * spos.z) + 1;
+  V3<R> dl = cand_pos - spos;
   R ld = (dl.x * dl.x + dl.y * dl.y) + dl.z * dl.z;
   if (!nearly_equal(la, lb, ld)) return false;
-  if (dot3(d, sk.normal) > 0) return cand_inside != sk.inside;
+  if (dot3(d, snrm) > 0) return cand_inside != sk.inside;
   return cand_inside == sk.inside;
 }
 
@@ -481,17 +487,16 @@ struct Best {
   int which;
 };
 
-template <typename R, bool COUNT>
+template <typename R>
 __device__ __forceinline__ void test_leaf(const SceneView<R>& sc, uint32_t ref, R leaf_near, const V3<R>& o, const V3<R>& d,
-                                          const Skip<R>& sk, Best<R>& best, uint32_t& n_prims) {
-  if (COUNT) n_prims++;
+                                          const Skip<R>& sk, Best<R>& best) {
   Cand<R> c[2];
   int n = prim_hits<R, false>(sc, ref, o, d, c);
   const uint32_t slot = ref & REF_SLOT_MASK;
   for (int i = 0; i < n; i++) {  // Primitive.RayTrace, Primitives/Primitive.cs:46-75
     bool inside = c[i].inside ^ ((ref & REF_INVERT) != 0);  // :60-61, Hit.cs:39-42
     if (inside && !(ref & REF_TWOSIDED)) continue;          // :63-64
-    if (slot == sk.slot && skip_matches<R>(sc, ref, o, d, i, inside, c[i], sk)) continue;  // :66
+    if (slot == sk.slot && skip_matches<R>(sc, ref, o, d, i, inside, c[i].t, c[i].pos, sk)) continue;  // :66
     R t = c[i].t;
     // Scene.cs:85-86 strict `<`; equal distances fall back to the reference's scan order (Near, then leaf order).
     // A candidate whose distance is NaN or +inf (the reference's det == 0 artefacts) is never taken.
@@ -507,68 +512,6 @@ __device__ __forceinline__ void test_leaf(const SceneView<R>& sc, uint32_t ref, 
       best.which = i;
     }
     break;  // :68-70 first acceptable hit of this primitive
-  }
-}
-
-template <typename R, bool COUNT>
-__device__ __forceinline__ void trace_one(const SceneView<R>& sc, const V3<R>& o, const V3<R>& d, const Skip<R>& sk,
-                                          Best<R>& best, uint32_t& n_nodes, uint32_t& n_prims) {
-  V3<R> inv = mk3(rrcp(d.x), rrcp(d.y), rrcp(d.z));
-  if constexpr (Num<R>::is_f64) inv = mk3(R(1) / d.x, R(1) / d.y, R(1) / d.z);  // AABB.cs:129
-  uint32_t stack_node[kTraceStack];
-  R stack_near[kTraceStack];
-  int sp = 0;
-  best.t = Num<R>::inf();
-  best.near_ = 0;
-  best.ref = 0xFFFFFFFFu;
-  best.which = 0;
-  uint32_t node = sc.root;
-  for (;;) {
-    const DNode<R>* np = sc.nodes + node;
-    V4<R> n0 = ldg4(&np->n0), n1 = ldg4(&np->n1), nz = ldg4(&np->nz);
-    uint2 ch = __ldg(reinterpret_cast<const uint2*>(&np->left));
-    if (COUNT) n_nodes++;
-    R nl, nr;
-    bool hl = (ch.x != REF_EMPTY) && box_test<R>(n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, o, d, inv, nl);
-    bool hr = (ch.y != REF_EMPTY) && box_test<R>(n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, o, d, inv, nr);
-    hl = hl && !(nl > best.t);
-    hr = hr && !(nr > best.t);
-    uint32_t c0 = ch.x, c1 = ch.y;
-    if (hl && hr) {
-      if (nr < nl) {
-        uint32_t tc = c0; c0 = c1; c1 = tc;
-        R tn = nl; nl = nr; nr = tn;
-      }
-    } else if (hr) {
-      c0 = c1;
-      nl = nr;
-      hl = true;
-      hr = false;
-    }
-    uint32_t next = 0xFFFFFFFFu;
-    if (hl) {
-      if (c0 & REF_LEAF)
-        test_leaf<R, COUNT>(sc, c0, nl, o, d, sk, best, n_prims);
-      else
-        next = c0;
-    }
-    if (hr && !(nr > best.t)) {
-      if (c1 & REF_LEAF) {
-        test_leaf<R, COUNT>(sc, c1, nr, o, d, sk, best, n_prims);
-      } else if (next == 0xFFFFFFFFu) {
-        next = c1;
-      } else {
-        stack_node[sp] = c1;
-        stack_near[sp] = nr;
-        sp++;
-      }
-    }
-    while (next == 0xFFFFFFFFu) {
-      if (sp == 0) return;
-      sp--;
-      if (!(stack_near[sp] > best.t)) next = stack_node[sp];
-    }
-    node = next;
   }
 }
 
@@ -635,6 +578,7 @@ __device__ __forceinline__ void band_pixel(const Band& b, uint32_t path, int& x,
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStreamThreads = 256;
 constexpr int kTraceThreads = 128;
+constexpr int kTraceMinBlocks = 6;
 
 // raygen: one thread per path of the band. Writes the bounce-0 ray (already re-normalised as GetColor does for
 // i % 3 == 0, Raytracer.cs:74-75), tint = 1 and an empty skip hit.
@@ -672,52 +616,168 @@ __global__ void __launch_bounds__(kStreamThreads) k_camera_rays(CameraView<R> ca
   out[i].dir[0] = d.x; out[i].dir[1] = d.y; out[i].dir[2] = d.z;
 }
 
-// trace: persistent warps pull 32 queue entries at a time from a global cursor (dynamic balancing of rays whose
-// traversal lengths differ by orders of magnitude), one ray per lane.
+// trace: persistent warps, one ray per lane, scheduled warp-synchronously. On sm_70+ a per-lane `while` nest is not
+// re-converged at loop exits and degenerates into lanes issuing one at a time, so the kernel is written as ONE
+// warp-uniform loop whose every iteration runs exactly one of three bodies, chosen by warp vote:
+//   refill  lanes whose ray is finished write its Hit record and take the next queue entries (one warp-aggregated
+//           atomicAdd on a global cursor); taken when more than 32 - kRefill lanes are idle (Aila & Laine 2009);
+//   node    lanes standing on an inner node fetch it (4 x 16-byte loads), test both child boxes, descend to the
+//           nearer child and push the farther one;
+//   leaf    lanes standing on a leaf test its primitive and pop their next stack entry.
+// node vs leaf is greedy: whichever has more lanes ready runs, the other lanes wait. Leaves are ~1 in 16 steps of a
+// ray, so a plain while-while loop (all lanes reach a leaf before any is tested) leaves ~3/4 of the lanes idle.
+// The per-lane stack holds (node, box near) pairs so stale entries are discarded without fetching the node.
+constexpr int kRefill = 24;
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+template <typename R>
+__device__ __forceinline__ void stack_pop(const uint32_t* stack_node, const R* stack_near, int& sp, R best_t, uint32_t& cur,
+                                          R& cur_near) {
+  cur = kNone;
+  while (sp > 0) {
+    sp--;
+    if (!(stack_near[sp] > best_t)) {
+      cur = stack_node[sp];
+      cur_near = stack_near[sp];
+      break;
+    }
+  }
+}
+
 template <typename R, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads) k_trace(SceneView<R> sc, PathView<R> pv, int q, int prev, int cur,
-                                                          int identity_queue) {
+__global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinBlocks) k_trace(SceneView<R> sc, PathView<R> pv, int q, int prev,
+                                                                           int cur_buf, int identity_queue) {
   const uint32_t count = pv.ctl->count[q];
   const uint32_t* queue = pv.queue[q];
   const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   uint32_t n_nodes = 0, n_prims = 0;
+  uint32_t stack_node[kTraceStack];
+  R stack_near[kTraceStack];
+  bool active = false;      // the lane holds an unfinished ray
+  bool finished = false;    // the lane holds a finished ray whose Hit record is not written yet
+  bool exhausted = false;   // warp-uniform: the queue has no more entries
+  uint32_t path = 0;
+  V3<R> o = mk3(R(0), R(0), R(0)), d = o, inv = o;
+  Skip<R> sk;
+  sk.slot = REF_SLOT_MASK + 1;
+  sk.inside = false;
+  sk.hpos = sk.hnrm = sk.spos = nullptr;
+  Best<R> best;
+  best.t = Num<R>::inf();
+  best.near_ = 0;
+  best.ref = kNone;
+  best.which = 0;
+  int sp = 0;
+  uint32_t cur = kNone;
+  R cur_near = 0;
+
   for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&pv.ctl->work_trace, 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= count) break;
-    uint32_t idx = base + lane;
-    if (idx < count) {
-      uint32_t path = identity_queue ? idx : queue[idx];
-      V4<R> dv = ld4(&pv.dir[path]);
-      V4<R> op = ld4(&pv.hpos[prev][path]);
-      V4<R> sn = ld4(&pv.hnrm[prev][path]);
-      V3<R> o = xyz(op), d = xyz(dv);
-      Skip<R> sk;
-      uint32_t code = code_of(sn.w);
-      sk.slot = (code == HIT_MISS) ? (REF_SLOT_MASK + 1) : (code & REF_SLOT_MASK);
-      sk.inside = (code & HIT_INSIDE) != 0;
-      sk.t = op.w;
-      sk.normal = xyz(sn);
-      sk.pos = o;
-      if (pv.skip_pos) sk.pos = xyz(ld4(&pv.skip_pos[path]));
-      Best<R> best;
-      trace_one<R, COUNT>(sc, o, d, sk, best, n_nodes, n_prims);
-      if (best.ref == 0xFFFFFFFFu) {
-        R w;
-        set_code(w, HIT_MISS);
-        st4(&pv.hpos[cur][path], R(0), R(0), R(0), R(0));
-        st4(&pv.hnrm[cur][path], R(0), R(0), R(0), w);
-      } else {
-        Cand<R> c[2];
-        prim_hits<R, true>(sc, best.ref, o, d, c);
-        const Cand<R>& h = c[best.which];
-        bool inside = h.inside ^ ((best.ref & REF_INVERT) != 0);
-        R w;
-        set_code(w, (best.ref & REF_SLOT_MASK) | (inside ? HIT_INSIDE : 0u));
-        st4(&pv.hpos[cur][path], h.pos.x, h.pos.y, h.pos.z, h.t);
-        st4(&pv.hnrm[cur][path], h.normal.x, h.normal.y, h.normal.z, w);
+    const unsigned m_idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if (m_idle == 0xFFFFFFFFu || (!exhausted && __popc(m_idle) > 32 - kRefill)) {
+      // ---- refill ------------------------------------------------------------------------------------------
+      if (finished) {  // Hit record for the shade kernel / next bounce's skip hit
+        if (best.ref == kNone) {
+          R w;
+          set_code(w, HIT_MISS);
+          st4(&pv.hpos[cur_buf][path], R(0), R(0), R(0), R(0));
+          st4(&pv.hnrm[cur_buf][path], R(0), R(0), R(0), w);
+        } else {
+          Cand<R> c[2];
+          prim_hits<R, true>(sc, best.ref, o, d, c);
+          const Cand<R>& h = c[best.which];
+          const bool inside = h.inside ^ ((best.ref & REF_INVERT) != 0);
+          R w;
+          set_code(w, (best.ref & REF_SLOT_MASK) | (inside ? HIT_INSIDE : 0u));
+          st4(&pv.hpos[cur_buf][path], h.pos.x, h.pos.y, h.pos.z, h.t);
+          st4(&pv.hnrm[cur_buf][path], h.normal.x, h.normal.y, h.normal.z, w);
+        }
+        finished = false;
       }
+      if (exhausted) {
+        if (m_idle == 0xFFFFFFFFu) break;
+        continue;
+      }
+      uint32_t base = 0;
+      const int leader = __ffs(m_idle) - 1;
+      if (lane == leader) base = atomicAdd(&pv.ctl->work_trace, (uint32_t)__popc(m_idle));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      bool got = true;
+      if (!active) {
+        const uint32_t idx = base + __popc(m_idle & lt_mask);
+        got = idx < count;
+        if (got) {
+          path = identity_queue ? idx : queue[idx];
+          V4<R> dv = ld4(&pv.dir[path]);
+          V4<R> op = ld4(&pv.hpos[prev][path]);
+          const uint32_t code = code_of(pv.hnrm[prev][path].w);
+          o = xyz(op);
+          d = xyz(dv);
+          if constexpr (Num<R>::is_f64)
+            inv = mk3(R(1) / d.x, R(1) / d.y, R(1) / d.z);  // AABB.cs:129
+          else
+            inv = mk3(rrcp(d.x), rrcp(d.y), rrcp(d.z));
+          sk.slot = (code == HIT_MISS) ? (REF_SLOT_MASK + 1) : (code & REF_SLOT_MASK);
+          sk.inside = (code & HIT_INSIDE) != 0;
+          sk.hpos = &pv.hpos[prev][path];
+          sk.hnrm = &pv.hnrm[prev][path];
+          sk.spos = pv.skip_pos ? &pv.skip_pos[path] : nullptr;
+          best.t = Num<R>::inf();
+          best.near_ = 0;
+          best.ref = kNone;
+          best.which = 0;
+          sp = 0;
+          cur = sc.root;
+          cur_near = 0;
+          active = true;
+        }
+      }
+      exhausted = !__all_sync(0xFFFFFFFFu, got);
+      continue;
+    }
+
+    const unsigned m_node = __ballot_sync(0xFFFFFFFFu, active && !(cur & REF_LEAF));
+    const unsigned m_leaf = ~(m_node | m_idle);
+    if (__popc(m_node) >= __popc(m_leaf)) {
+      // ---- node step ---------------------------------------------------------------------------------------
+      if (active && !(cur & REF_LEAF)) {
+        const DNode<R>* np = sc.nodes + cur;
+        V4<R> n0 = ldg4(&np->n0), n1 = ldg4(&np->n1), nz = ldg4(&np->nz);
+        uint2 ch = __ldg(reinterpret_cast<const uint2*>(&np->left));
+        if (COUNT) n_nodes++;
+        R nl, nr;
+        bool hl = box_test<R>(n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, o, d, inv, nl) && (ch.x != REF_EMPTY);
+        bool hr = box_test<R>(n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, o, d, inv, nr) && (ch.y != REF_EMPTY);
+        hl = hl && !(nl > best.t);
+        hr = hr && !(nr > best.t);
+        if (hl && hr) {
+          const bool swap = nr < nl;
+          stack_node[sp] = swap ? ch.x : ch.y;
+          stack_near[sp] = swap ? nl : nr;
+          sp++;
+          cur = swap ? ch.y : ch.x;
+          cur_near = swap ? nr : nl;
+        } else if (hl) {
+          cur = ch.x;
+          cur_near = nl;
+        } else if (hr) {
+          cur = ch.y;
+          cur_near = nr;
+        } else {
+          stack_pop<R>(stack_node, stack_near, sp, best.t, cur, cur_near);
+        }
+      }
+    } else {
+      // ---- leaf step ---------------------------------------------------------------------------------------
+      if (active && (cur & REF_LEAF)) {
+        if (COUNT) n_prims++;
+        test_leaf<R>(sc, cur, cur_near, o, d, sk, best);
+        stack_pop<R>(stack_node, stack_near, sp, best.t, cur, cur_near);
+      }
+    }
+    if (active && cur == kNone) {
+      active = false;
+      finished = true;
     }
   }
   if (COUNT) {

@@ -47,6 +47,10 @@ class Context:
     def set_option(self, opt, value):
         self._ck(N.lib.rtc_set_option(self._h, opt, int(value)))
 
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        self._ck(N.lib.rtc_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
     # -- scene hand-over ---------------------------------------------------------------------------------
     def upload_scene(self, scene_or_desc):
         d = scene_or_desc.desc() if isinstance(scene_or_desc, Scene) else scene_or_desc

@@ -1,0 +1,48 @@
+"""Profiling helper: one workload, a few passes, per-kernel event times and traversal counters.
+Used under ncu on the GPU box (see profiles/README.md)."""
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from raytracercore_b200 import RTC_F32, RTC_F64, RTC_OPT_COUNTERS, RTC_OPT_KERNEL_TIMING, RTC_OPT_MAX_PATHS, Context  # noqa: E402
+from raytracercore_b200 import _native as N  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="soup1m")
+ap.add_argument("--spp", type=int, default=1)
+ap.add_argument("--passes", type=int, default=2)
+ap.add_argument("--size", type=int, default=0, help="override width=height")
+ap.add_argument("--precision", default="f32")
+ap.add_argument("--counters", action="store_true")
+ap.add_argument("--max-paths", type=int, default=0)
+a = ap.parse_args()
+sc = bench.make_scene(a.workload)
+if a.size:
+    sc.override(width=a.size, height=a.size)
+ctx = Context(0, RTC_F64 if a.precision == "f64" else RTC_F32)
+if a.max_paths:
+    ctx.set_option(RTC_OPT_MAX_PATHS, a.max_paths)
+ctx.load(sc, seed=1)
+ctx.render(0, a.spp)
+ctx.sync()
+ctx.reset_stats()
+ctx.set_option(RTC_OPT_KERNEL_TIMING, 1)
+if a.counters:
+    ctx.set_option(RTC_OPT_COUNTERS, 1)
+t = time.time()
+for i in range(a.passes):
+    ctx.render((1 + i) * a.spp, a.spp)
+ctx.sync()
+dt = time.time() - t
+st = ctx.stats()
+print("wall %.3f s  paths %d rays %d  -> %.1f Mrays/s (wall)" % (dt, st.paths, st.rays, st.rays / dt / 1e6))
+for k in range(N.RTC_K_COUNT):
+    print("  %-10s launches %4d  ms %9.3f" % (N.KERNEL_NAMES[k], st.launches[k], st.ms[k]))
+if st.ms[N.RTC_K_TRACE] > 0:
+    print("trace-only Mrays/s: %.1f" % (st.rays / st.ms[N.RTC_K_TRACE] / 1e3))
+if a.counters:
+    print("nodes/ray %.1f prims/ray %.2f" % (st.nodes_visited / st.rays, st.prims_tested / st.rays))
