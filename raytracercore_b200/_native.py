@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtcore_b200.so")
+LIB_PATH = os.environ.get("RTC_B200_LIB") or os.path.join(_HERE, "librtcore_b200.so")  # env override: kernel-variant A/B runs
 
 RTC_OK, RTC_ERR_INVALID, RTC_ERR_CUDA, RTC_ERR_STATE, RTC_ERR_NOMEM, RTC_ERR_UNSUPPORTED, RTC_ERR_NCCL = range(7)
 RTC_F32, RTC_F64 = 0, 1

@@ -41,6 +41,21 @@ def _run(cmd):
     return r.stdout
 
 
+def build_variant(name, defines):
+    """Development aid: build lib variant `name` with extra -D flags (kernel tuning A/B runs via RTC_B200_LIB)."""
+    global OBJ, LIB
+    old = (OBJ, LIB)
+    OBJ = os.path.join(HERE, "_obj_" + name)
+    LIB = os.path.join(HERE, "librtcore_b200_%s.so" % name)
+    extra = os.environ.get("RTC_EXTRA_NVCC", "")
+    os.environ["RTC_EXTRA_NVCC"] = " ".join(defines)
+    try:
+        return build(force=True)
+    finally:
+        os.environ["RTC_EXTRA_NVCC"] = extra
+        OBJ, LIB = old
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
@@ -61,7 +76,8 @@ def build(force=False, verbose=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src + ".o")
         if force or _newer(o, [s] + headers):
-            out = _run([nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            extra = os.environ.get("RTC_EXTRA_NVCC", "").split()
+            out = _run([nvcc] + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
             if verbose:
                 print(out)
         objs.append(o)

@@ -268,9 +268,11 @@ template <typename R>
 R round_down(double x) {
   if constexpr (std::is_same<R, double>::value) return x;
   else {
+    // round toward -inf, then one more ulp: the f32 slab test evaluates fma(bound, 1/d, -o/d), whose rounding is
+    // equivalent to moving the bound by up to an ulp of the coordinate magnitude
     float f = (float)x;
     if ((double)f > x) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
-    return f;
+    return std::nextafterf(f, -std::numeric_limits<float>::infinity());
   }
 }
 template <typename R>
@@ -279,7 +281,7 @@ R round_up(double x) {
   else {
     float f = (float)x;
     if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
-    return f;
+    return std::nextafterf(f, std::numeric_limits<float>::infinity());
   }
 }
 
@@ -292,40 +294,35 @@ int build_device_scene(rtc_ctx* ctx) {
   if (ctx->root < 0 || ctx->root >= nn) return fail(ctx, RTC_ERR_INVALID, "BVH root out of range");
   if (n > (int32_t)REF_SLOT_MASK) return fail(ctx, RTC_ERR_UNSUPPORTED, "more than 2^26-1 primitives");
 
-  std::vector<int32_t> inner_idx(nn, -1), leaf_slot(nn, -1);
+  // Pass 1: validate the tree and number the leaves in left-first order (BVH.cs:314-315): slot == leaf order.
+  std::vector<int32_t> leaf_slot(nn, -1);
   std::vector<int32_t> slot_prim;
   slot_prim.reserve(n);
-  std::vector<uint8_t> prim_seen(n, 0);
-  struct It {
-    int32_t node, depth;
-  };
-  std::vector<It> st;
-  st.push_back({ctx->root, 0});
-  int32_t n_inner = 0, visited = 0, max_depth = 0;
-  while (!st.empty()) {
-    It it = st.back();
-    st.pop_back();
-    if (++visited > nn) return fail(ctx, RTC_ERR_INVALID, "BVH is not a tree (node reached twice)");
-    const rtc_bvh_node& nd = nodes[it.node];
-    max_depth = std::max(max_depth, it.depth);
-    if (nd.prim >= 0) {
-      if (nd.prim >= n) return fail(ctx, RTC_ERR_INVALID, "BVH leaf references a primitive out of range");
-      if (prim_seen[nd.prim]) return fail(ctx, RTC_ERR_INVALID, "primitive referenced by two BVH leaves");
-      prim_seen[nd.prim] = 1;
-      leaf_slot[it.node] = (int32_t)slot_prim.size();
-      slot_prim.push_back(nd.prim);
-    } else {
-      if (nd.left < 0 || nd.left >= nn || nd.right < 0 || nd.right >= nn)
-        return fail(ctx, RTC_ERR_INVALID, "BVH child index out of range");
-      if (inner_idx[it.node] >= 0) return fail(ctx, RTC_ERR_INVALID, "BVH is not a tree (node reached twice)");
-      inner_idx[it.node] = n_inner++;
-      st.push_back({nd.right, it.depth + 1});
-      st.push_back({nd.left, it.depth + 1});  // left is processed first: left-first leaf order (BVH.cs:314-315)
+  std::vector<uint8_t> prim_seen(n, 0), node_seen(nn, 0);
+  {
+    std::vector<int32_t> st;
+    st.push_back(ctx->root);
+    while (!st.empty()) {
+      int32_t i = st.back();
+      st.pop_back();
+      if (node_seen[i]) return fail(ctx, RTC_ERR_INVALID, "BVH is not a tree (node reached twice)");
+      node_seen[i] = 1;
+      const rtc_bvh_node& nd = nodes[i];
+      if (nd.prim >= 0) {
+        if (nd.prim >= n) return fail(ctx, RTC_ERR_INVALID, "BVH leaf references a primitive out of range");
+        if (prim_seen[nd.prim]) return fail(ctx, RTC_ERR_INVALID, "primitive referenced by two BVH leaves");
+        prim_seen[nd.prim] = 1;
+        leaf_slot[i] = (int32_t)slot_prim.size();
+        slot_prim.push_back(nd.prim);
+      } else {
+        if (nd.left < 0 || nd.left >= nn || nd.right < 0 || nd.right >= nn)
+          return fail(ctx, RTC_ERR_INVALID, "BVH child index out of range");
+        st.push_back(nd.right);
+        st.push_back(nd.left);
+      }
     }
   }
   if ((int32_t)slot_prim.size() != n) return fail(ctx, RTC_ERR_INVALID, "BVH does not reference every primitive exactly once");
-  if (max_depth + 2 > kTraceStack) return fail(ctx, RTC_ERR_UNSUPPORTED, "BVH depth " + std::to_string(max_depth) + " exceeds the traversal stack (" + std::to_string(kTraceStack) + ")");
-  ctx->bvh_depth = max_depth;
 
   auto leaf_ref = [&](int32_t node) -> uint32_t {
     int32_t p = nodes[node].prim;
@@ -337,36 +334,98 @@ int build_device_scene(rtc_ctx* ctx) {
     if (f & RTC_FLAG_INVERT) r |= REF_INVERT;
     return r;
   };
-  auto child_ref = [&](int32_t node) -> uint32_t { return nodes[node].prim >= 0 ? leaf_ref(node) : (uint32_t)inner_idx[node]; };
 
-  const bool single_leaf = nodes[ctx->root].prim >= 0;
-  std::vector<DNode<R>> dn(single_leaf ? 1 : n_inner);
-  auto set_box = [&](DNode<R>& d, int side, const rtc_bvh_node& c) {
-    R lox = round_down<R>(c.bmin[0]), hix = round_up<R>(c.bmax[0]);
-    R loy = round_down<R>(c.bmin[1]), hiy = round_up<R>(c.bmax[1]);
-    R loz = round_down<R>(c.bmin[2]), hiz = round_up<R>(c.bmax[2]);
-    V4<R>& nxy = side == 0 ? d.n0 : d.n1;
-    nxy.x = lox; nxy.y = hix; nxy.z = loy; nxy.w = hiy;
-    if (side == 0) { d.nz.x = loz; d.nz.y = hiz; } else { d.nz.z = loz; d.nz.w = hiz; }
+  // Pass 2: collapse the binary tree into W-wide nodes. A wide node starts from the two children of a binary
+  // node and repeatedly replaces its largest-area inner child by that child's two children (in place, so the
+  // left-to-right order is kept) until it has W children or only leaves.
+  constexpr int W = Width<R>::value;
+  auto area = [&](int32_t i) -> double {
+    const rtc_bvh_node& c = nodes[i];
+    double dx = c.bmax[0] - c.bmin[0], dy = c.bmax[1] - c.bmin[1], dz = c.bmax[2] - c.bmin[2];
+    double a = (dx * dy + dy * dz + dz * dx) * 2;
+    return std::isfinite(a) ? a : std::numeric_limits<double>::max();
   };
-  if (single_leaf) {
+  std::vector<DNode<R>> dn;
+  dn.reserve((size_t)std::max(1, nn / W + 16));
+  auto set_box = [&](DNode<R>& d, int c, const rtc_bvh_node& b) {
+    for (int a = 0; a < 3; a++) {
+      d.lo[a][c] = round_down<R>(b.bmin[a]);
+      d.hi[a][c] = round_up<R>(b.bmax[a]);
+    }
+  };
+  auto set_empty = [&](DNode<R>& d, int c) {
+    for (int a = 0; a < 3; a++) {
+      d.lo[a][c] = std::numeric_limits<R>::infinity();
+      d.hi[a][c] = -std::numeric_limits<R>::infinity();
+    }
+    d.child[c] = REF_EMPTY;
+  };
+  struct Work {
+    int32_t bnode;      // binary node this wide node stands for
+    int32_t parent;     // wide parent index (-1 for the root)
+    int32_t pslot;      // child slot in the parent
+    int32_t stack_use;  // stack entries pending above this node
+  };
+  std::vector<Work> work;
+  int32_t max_stack = 0;
+  if (nodes[ctx->root].prim >= 0) {
+    dn.emplace_back();
     std::memset(&dn[0], 0, sizeof(DNode<R>));
     set_box(dn[0], 0, nodes[ctx->root]);
-    dn[0].left = leaf_ref(ctx->root);
-    dn[0].right = REF_EMPTY;
-    ctx->root_node = 0;
+    dn[0].child[0] = leaf_ref(ctx->root);
+    for (int c = 1; c < W; c++) set_empty(dn[0], c);
   } else {
-    for (int32_t i = 0; i < nn; i++) {
-      if (inner_idx[i] < 0) continue;
-      DNode<R>& d = dn[inner_idx[i]];
-      std::memset(&d, 0, sizeof(d));
-      set_box(d, 0, nodes[nodes[i].left]);
-      set_box(d, 1, nodes[nodes[i].right]);
-      d.left = child_ref(nodes[i].left);
-      d.right = child_ref(nodes[i].right);
+    work.push_back({ctx->root, -1, 0, 0});
+    while (!work.empty()) {
+      Work wk = work.back();
+      work.pop_back();
+      int32_t kids[W];
+      int nk = 2;
+      kids[0] = nodes[wk.bnode].left;
+      kids[1] = nodes[wk.bnode].right;
+      while (nk < W) {
+        int best = -1;
+        double best_a = -1;
+        for (int c = 0; c < nk; c++)
+          if (nodes[kids[c]].prim < 0) {
+            double a = area(kids[c]);
+            if (a > best_a) {
+              best_a = a;
+              best = c;
+            }
+          }
+        if (best < 0) break;
+        int32_t e = kids[best];
+        for (int c = nk; c > best + 1; c--) kids[c] = kids[c - 1];
+        kids[best] = nodes[e].left;
+        kids[best + 1] = nodes[e].right;
+        nk++;
+      }
+      const int32_t me = (int32_t)dn.size();
+      dn.emplace_back();
+      std::memset(&dn[me], 0, sizeof(DNode<R>));
+      if (wk.parent >= 0) dn[wk.parent].child[wk.pslot] = (uint32_t)me;
+      const int32_t use = wk.stack_use + (nk - 1);
+      max_stack = std::max(max_stack, use);
+      for (int c = 0; c < W; c++) {
+        if (c >= nk) {
+          set_empty(dn[me], c);
+          continue;
+        }
+        set_box(dn[me], c, nodes[kids[c]]);
+        if (nodes[kids[c]].prim >= 0)
+          dn[me].child[c] = leaf_ref(kids[c]);
+        else
+          dn[me].child[c] = REF_EMPTY;  // patched when the child node is emitted
+      }
+      for (int c = nk - 1; c >= 0; c--)  // left child emitted next: depth-first layout
+        if (nodes[kids[c]].prim < 0) work.push_back({kids[c], me, c, use});
     }
-    ctx->root_node = (uint32_t)inner_idx[ctx->root];
   }
+  ctx->root_node = 0;
+  if (max_stack + 2 > kTraceStack)
+    return fail(ctx, RTC_ERR_UNSUPPORTED, "BVH needs " + std::to_string(max_stack) + " traversal stack entries, limit is " + std::to_string(kTraceStack - 2));
+  ctx->bvh_depth = max_stack;
 
   std::vector<DPrim<R>> dp(n);
   std::vector<DMat<R>> dm(n);
@@ -376,6 +435,7 @@ int build_device_scene(rtc_ctx* ctx) {
     if (leaf_slot[i] < 0) continue;
     prim_ref[leaf_slot[i]] = leaf_ref(i);
   }
+  (void)node_seen;
   for (int32_t s = 0; s < n; s++) {
     int32_t p = slot_prim[s];
     prim_id[s] = p;

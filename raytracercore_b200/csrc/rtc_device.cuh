@@ -38,6 +38,11 @@ __device__ __forceinline__ float rsqrt_(float a) { return sqrtf(a); }
 __device__ __forceinline__ double rsqrt_(double a) { return sqrt(a); }
 __device__ __forceinline__ float rrcp(float a) { return __frcp_rn(a); }
 __device__ __forceinline__ double rrcp(double a) { return 1.0 / a; }
+__device__ __forceinline__ float clamped_rcp(float a) {
+  float r = __frcp_rn(a);
+  return fabsf(r) <= 0x1.0p64f ? r : copysignf(0x1.0p64f, a);  // also maps the NaN of 1/NaN away
+}
+__device__ __forceinline__ double clamped_rcp(double a) { return 1.0 / a; }
 __device__ __forceinline__ float rpow(float a, float b) { return powf(a, b); }
 __device__ __forceinline__ double rpow(double a, double b) { return pow(a, b); }
 __device__ __forceinline__ float racos(float a) { return acosf(a); }
@@ -129,6 +134,76 @@ template <typename R>
 __device__ __forceinline__ void st4(V4<R>* p, R x, R y, R z, R w) {
   V4<R> v; v.x = x; v.y = y; v.z = z; v.w = w;
   *p = v;
+}
+
+// One row of a wide BVH node (W values of R) with the widest loads the row size allows.
+__device__ __forceinline__ void unpack4(const uint4& t, float* o) {
+  o[0] = __uint_as_float(t.x); o[1] = __uint_as_float(t.y); o[2] = __uint_as_float(t.z); o[3] = __uint_as_float(t.w);
+}
+__device__ __forceinline__ void unpack4(const uint4& t, double* o) {
+  o[0] = __hiloint2double((int)t.y, (int)t.x);
+  o[1] = __hiloint2double((int)t.w, (int)t.z);
+}
+template <typename R, int W>
+__device__ __forceinline__ void load_row(const R* p, R (&out)[W]) {
+  constexpr int bytes = W * (int)sizeof(R);
+  if constexpr (bytes % 16 == 0) {
+#pragma unroll
+    for (int i = 0; i < bytes / 16; i++) {
+      uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + i);
+      unpack4(t, &out[i * (16 / (int)sizeof(R))]);
+    }
+  } else {
+    static_assert(bytes == 8, "unsupported node row size");
+    uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    out[0] = __uint_as_float(t.x);
+    out[1] = __uint_as_float(t.y);
+  }
+}
+template <int W>
+__device__ __forceinline__ void load_children(const uint32_t* p, uint32_t (&out)[W]) {
+  if constexpr (W % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < W / 4; i++) {
+      uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + i);
+      out[4 * i] = t.x; out[4 * i + 1] = t.y; out[4 * i + 2] = t.z; out[4 * i + 3] = t.w;
+    }
+  } else {
+    uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    out[0] = t.x;
+    out[1] = t.y;
+  }
+}
+
+// compare-exchange networks that sort W (key, value) pairs ascending by key
+template <typename R>
+__device__ __forceinline__ void cswap(R& ka, uint32_t& va, R& kb, uint32_t& vb) {
+  const bool s = kb < ka;
+  const R tk = s ? kb : ka;
+  const uint32_t tv = s ? vb : va;
+  kb = s ? ka : kb;
+  vb = s ? va : vb;
+  ka = tk;
+  va = tv;
+}
+template <typename R, int W>
+__device__ __forceinline__ void sort_children(R (&k)[W], uint32_t (&v)[W]) {
+#define RTC_CS(a, b) cswap(k[a], v[a], k[b], v[b])
+  if constexpr (W == 2) {
+    RTC_CS(0, 1);
+  } else if constexpr (W == 4) {
+    RTC_CS(0, 1); RTC_CS(2, 3); RTC_CS(0, 2); RTC_CS(1, 3); RTC_CS(1, 2);
+  } else {
+    static_assert(W == 8, "unsupported BVH width");
+    RTC_CS(0, 1); RTC_CS(2, 3); RTC_CS(4, 5); RTC_CS(6, 7);
+    RTC_CS(0, 2); RTC_CS(1, 3); RTC_CS(4, 6); RTC_CS(5, 7);
+    RTC_CS(1, 2); RTC_CS(5, 6); RTC_CS(0, 4); RTC_CS(3, 7);
+    RTC_CS(1, 5); RTC_CS(2, 6);
+    RTC_CS(1, 4); RTC_CS(3, 6);
+    RTC_CS(2, 4); RTC_CS(3, 5);
+    RTC_CS(3, 4);
+  }
+#undef RTC_CS
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -577,8 +652,17 @@ __device__ __forceinline__ void band_pixel(const Band& b, uint32_t path, int& x,
 // Kernels
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStreamThreads = 256;
-constexpr int kTraceThreads = 128;
-constexpr int kTraceMinBlocks = 6;
+#ifndef RTC_TRACE_THREADS
+#define RTC_TRACE_THREADS 128
+#endif
+#ifndef RTC_TRACE_MIN_BLOCKS
+#define RTC_TRACE_MIN_BLOCKS 6
+#endif
+#ifndef RTC_PREFETCH
+#define RTC_PREFETCH 0
+#endif
+constexpr int kTraceThreads = RTC_TRACE_THREADS;
+constexpr int kTraceMinBlocks = RTC_TRACE_MIN_BLOCKS;
 
 // raygen: one thread per path of the band. Writes the bounce-0 ray (already re-normalised as GetColor does for
 // i % 3 == 0, Raytracer.cs:74-75), tint = 1 and an empty skip hit.
@@ -658,7 +742,8 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
   bool finished = false;    // the lane holds a finished ray whose Hit record is not written yet
   bool exhausted = false;   // warp-uniform: the queue has no more entries
   uint32_t path = 0;
-  V3<R> o = mk3(R(0), R(0), R(0)), d = o, inv = o;
+  V3<R> o = mk3(R(0), R(0), R(0)), d = o, inv = o, oinv = o;
+  uint32_t sgn = 0;
   Skip<R> sk;
   sk.slot = REF_SLOT_MASK + 1;
   sk.inside = false;
@@ -715,8 +800,13 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
           d = xyz(dv);
           if constexpr (Num<R>::is_f64)
             inv = mk3(R(1) / d.x, R(1) / d.y, R(1) / d.z);  // AABB.cs:129
-          else
-            inv = mk3(rrcp(d.x), rrcp(d.y), rrcp(d.z));
+          else {
+            // f32: slabs are evaluated as fma(bound, inv, -o*inv) on the bounds pre-selected by the direction's sign,
+            // so a zero component must not produce inf - inf: its reciprocal is clamped to +-2^64.
+            inv = mk3(clamped_rcp(d.x), clamped_rcp(d.y), clamped_rcp(d.z));
+            oinv = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+            sgn = (rsignbit(d.x) ? 1u : 0u) | (rsignbit(d.y) ? 2u : 0u) | (rsignbit(d.z) ? 4u : 0u);
+          }
           sk.slot = (code == HIT_MISS) ? (REF_SLOT_MASK + 1) : (code & REF_SLOT_MASK);
           sk.inside = (code & HIT_INSIDE) != 0;
           sk.hpos = &pv.hpos[prev][path];
@@ -741,28 +831,68 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
     if (__popc(m_node) >= __popc(m_leaf)) {
       // ---- node step ---------------------------------------------------------------------------------------
       if (active && !(cur & REF_LEAF)) {
+        constexpr int W = Width<R>::value;
         const DNode<R>* np = sc.nodes + cur;
-        V4<R> n0 = ldg4(&np->n0), n1 = ldg4(&np->n1), nz = ldg4(&np->nz);
-        uint2 ch = __ldg(reinterpret_cast<const uint2*>(&np->left));
+        uint32_t ch[W];
+        R key[W];
+        int nh = 0;
+        if constexpr (Num<R>::is_f64) {
+          R lo[3][W], hi[3][W];
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            load_row<R, W>(np->lo[a], lo[a]);
+            load_row<R, W>(np->hi[a], hi[a]);
+          }
+          load_children<W>(np->child, ch);
+#pragma unroll
+          for (int c = 0; c < W; c++) {
+            R nr;
+            bool h = box_test<R>(lo[0][c], hi[0][c], lo[1][c], hi[1][c], lo[2][c], hi[2][c], o, d, inv, nr);
+            h = h && (ch[c] != REF_EMPTY) && !(nr > best.t);
+            if (h && risnan(nr)) nr = -Num<R>::inf();
+            key[c] = h ? nr : Num<R>::inf();
+            nh += h ? 1 : 0;
+          }
+        } else {
+          // near / far bound rows picked by the ray's direction signs: no per-slab min/max
+          R bn[3][W], bf[3][W];
+          load_row<R, W>((sgn & 1u) ? np->hi[0] : np->lo[0], bn[0]);
+          load_row<R, W>((sgn & 1u) ? np->lo[0] : np->hi[0], bf[0]);
+          load_row<R, W>((sgn & 2u) ? np->hi[1] : np->lo[1], bn[1]);
+          load_row<R, W>((sgn & 2u) ? np->lo[1] : np->hi[1], bf[1]);
+          load_row<R, W>((sgn & 4u) ? np->hi[2] : np->lo[2], bn[2]);
+          load_row<R, W>((sgn & 4u) ? np->lo[2] : np->hi[2], bf[2]);
+          load_children<W>(np->child, ch);
+#pragma unroll
+          for (int c = 0; c < W; c++) {
+            const R tnx = fmaf(bn[0][c], inv.x, oinv.x), tny = fmaf(bn[1][c], inv.y, oinv.y), tnz = fmaf(bn[2][c], inv.z, oinv.z);
+            const R tfx = fmaf(bf[0][c], inv.x, oinv.x), tfy = fmaf(bf[1][c], inv.y, oinv.y), tfz = fmaf(bf[2][c], inv.z, oinv.z);
+            const R nr = fmaxf(fmaxf(tnx, tny), tnz);
+            const R fr = fminf(fminf(fminf(tfx, tfy), tfz), best.t);  // far >= 0 and near <= best.t folded in
+            const bool h = (nr <= fr) && (fr >= 0.0f);               // empty children have (+inf, -inf) boxes
+            key[c] = h ? nr : Num<R>::inf();
+            nh += h ? 1 : 0;
+          }
+        }
         if (COUNT) n_nodes++;
-        R nl, nr;
-        bool hl = box_test<R>(n0.x, n0.y, n0.z, n0.w, nz.x, nz.y, o, d, inv, nl) && (ch.x != REF_EMPTY);
-        bool hr = box_test<R>(n1.x, n1.y, n1.z, n1.w, nz.z, nz.w, o, d, inv, nr) && (ch.y != REF_EMPTY);
-        hl = hl && !(nl > best.t);
-        hr = hr && !(nr > best.t);
-        if (hl && hr) {
-          const bool swap = nr < nl;
-          stack_node[sp] = swap ? ch.x : ch.y;
-          stack_near[sp] = swap ? nl : nr;
-          sp++;
-          cur = swap ? ch.y : ch.x;
-          cur_near = swap ? nr : nl;
-        } else if (hl) {
-          cur = ch.x;
-          cur_near = nl;
-        } else if (hr) {
-          cur = ch.y;
-          cur_near = nr;
+        sort_children<R, W>(key, ch);  // hits first, nearest first (misses carry +inf keys)
+#pragma unroll
+        for (int c = W - 1; c >= 1; c--) {
+          if (c < nh) {  // farthest pushed first, so the nearest pending child is popped first
+#if RTC_PREFETCH
+            {
+              const void* pf = (ch[c] & REF_LEAF) ? (const void*)(sc.prims + (ch[c] & REF_SLOT_MASK)) : (const void*)(sc.nodes + ch[c]);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            }
+#endif
+            stack_node[sp] = ch[c];
+            stack_near[sp] = key[c];
+            sp++;
+          }
+        }
+        if (nh > 0) {
+          cur = ch[0];
+          cur_near = key[0];
         } else {
           stack_pop<R>(stack_node, stack_near, sp, best.t, cur, cur_near);
         }

@@ -2,7 +2,8 @@
 // and the two kernel translation units (kernels_f32.cu built with -fmad=true, kernels_f64.cu with -fmad=false).
 //
 // HBM layout (R = float in RTC_F32 mode, double in RTC_F64 mode; V4<R> is one 16-byte / 32-byte vector load):
-//   DNode<R>  4 x V4: both children's boxes + two child references. 64 B (f32): two nodes per 128-B line.
+//   DNode<R>  W children per node (W = 4 in f32 mode: 128 B = one cache line; W = 2 in f64 mode: 128 B), stored as
+//             lo[axis][child] / hi[axis][child] rows + W child references, so one 16-byte load = one bound of 4 children.
 //   DPrim<R>  3 x V4 per primitive, stored in left-first DFS leaf order so slot == leaf order (tie-break key):
 //               triangle  a=(v0.xyz,N.x) b=(e1.xyz,N.y) c=(e2.xyz,N.z)      (Triangle.cs:22-29)
 //               sphere    a=(center.xyz,radius)                              (Sphere.cs:11-14)
@@ -43,13 +44,29 @@ constexpr uint32_t Q_DEAD = 0x80000000u;  // queue entry flag written by shade f
 
 constexpr int kTraceStack = 128;
 
+// Branching factor of the device BVH. The reference's tree is binary (BVH.cs:239-254); for the device it is collapsed
+// into W-wide nodes (children of large-area inner nodes are pulled up) so that a ray makes ~log_W instead of log_2
+// dependent memory round trips. Leaves, their boxes and their left-first order are unchanged by the collapse.
 template <typename R>
-struct alignas(sizeof(R) * 4) DNode {
-  V4<R> n0;  // left child:  min.x max.x min.y max.y
-  V4<R> n1;  // right child: min.x max.x min.y max.y
-  V4<R> nz;  // left min.z max.z, right min.z max.z
-  uint32_t left, right, pad0, pad1;
+struct Width {
+  static constexpr int value = sizeof(R) == 4 ? 4 : 2;
 };
+
+constexpr int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <typename R, int W>
+struct alignas(next_pow2((6 * (int)sizeof(R) + 4) * W)) DNodeW {
+  R lo[3][W];  // lo[axis][child]: one vector load fetches one bound of every child
+  R hi[3][W];
+  uint32_t child[W];  // inner-node index, leaf reference, or REF_EMPTY
+};
+
+template <typename R>
+using DNode = DNodeW<R, Width<R>::value>;
 
 template <typename R>
 struct DPrim {
