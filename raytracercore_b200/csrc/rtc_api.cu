@@ -91,6 +91,9 @@ struct rtc_ctx {
   void *d_nodes = nullptr, *d_prims = nullptr, *d_xforms = nullptr, *d_mats = nullptr;
   int32_t *d_aux = nullptr, *d_prim_id = nullptr, *d_id_to_slot = nullptr;
   uint32_t* d_prim_ref = nullptr;
+  void* d_qnodes = nullptr;       // f32 mode: CNode[]
+  uint32_t* d_unbounded = nullptr;  // f32 mode: leaf refs of primitives with infinite boxes
+  int32_t n_unbounded = 0;
   uint32_t root_node = 0;
   int bvh_depth = 0;
 
@@ -157,6 +160,9 @@ void free_scene_device(rtc_ctx* c) {
   free_dev_t(c->d_prim_id);
   free_dev_t(c->d_id_to_slot);
   free_dev_t(c->d_prim_ref);
+  free_dev(c->d_qnodes);
+  free_dev_t(c->d_unbounded);
+  c->n_unbounded = 0;
 }
 
 void free_pool(rtc_ctx* c) {
@@ -224,6 +230,9 @@ SceneView<R> scene_view(rtc_ctx* c) {
   sv.prim_ref = c->d_prim_ref;
   sv.root = c->root_node;
   sv.n_prims = c->n_prims;
+  sv.qnodes = (const CNode*)c->d_qnodes;
+  sv.unbounded = c->d_unbounded;
+  sv.n_unbounded = c->n_unbounded;
   return sv;
 }
 
@@ -294,10 +303,10 @@ int build_device_scene(rtc_ctx* ctx) {
   if (ctx->root < 0 || ctx->root >= nn) return fail(ctx, RTC_ERR_INVALID, "BVH root out of range");
   if (n > (int32_t)REF_SLOT_MASK) return fail(ctx, RTC_ERR_UNSUPPORTED, "more than 2^26-1 primitives");
 
-  // Pass 1: validate the tree and number the leaves in left-first order (BVH.cs:314-315): slot == leaf order.
+  // Pass 1: validate the tree; collect the leaves in left-first order (BVH.cs:314-315).
   std::vector<int32_t> leaf_slot(nn, -1);
-  std::vector<int32_t> slot_prim;
-  slot_prim.reserve(n);
+  std::vector<int32_t> dfs_leaves;  // binary-tree leaf nodes, left first
+  dfs_leaves.reserve(n);
   std::vector<uint8_t> prim_seen(n, 0), node_seen(nn, 0);
   {
     std::vector<int32_t> st;
@@ -312,8 +321,7 @@ int build_device_scene(rtc_ctx* ctx) {
         if (nd.prim >= n) return fail(ctx, RTC_ERR_INVALID, "BVH leaf references a primitive out of range");
         if (prim_seen[nd.prim]) return fail(ctx, RTC_ERR_INVALID, "primitive referenced by two BVH leaves");
         prim_seen[nd.prim] = 1;
-        leaf_slot[i] = (int32_t)slot_prim.size();
-        slot_prim.push_back(nd.prim);
+        dfs_leaves.push_back(i);
       } else {
         if (nd.left < 0 || nd.left >= nn || nd.right < 0 || nd.right >= nn)
           return fail(ctx, RTC_ERR_INVALID, "BVH child index out of range");
@@ -322,7 +330,8 @@ int build_device_scene(rtc_ctx* ctx) {
       }
     }
   }
-  if ((int32_t)slot_prim.size() != n) return fail(ctx, RTC_ERR_INVALID, "BVH does not reference every primitive exactly once");
+  if ((int32_t)dfs_leaves.size() != n) return fail(ctx, RTC_ERR_INVALID, "BVH does not reference every primitive exactly once");
+  std::vector<int32_t> slot_prim(n, -1);
 
   auto leaf_ref = [&](int32_t node) -> uint32_t {
     int32_t p = nodes[node].prim;
@@ -334,98 +343,305 @@ int build_device_scene(rtc_ctx* ctx) {
     if (f & RTC_FLAG_INVERT) r |= REF_INVERT;
     return r;
   };
-
-  // Pass 2: collapse the binary tree into W-wide nodes. A wide node starts from the two children of a binary
-  // node and repeatedly replaces its largest-area inner child by that child's two children (in place, so the
-  // left-to-right order is kept) until it has W children or only leaves.
-  constexpr int W = Width<R>::value;
-  auto area = [&](int32_t i) -> double {
-    const rtc_bvh_node& c = nodes[i];
-    double dx = c.bmax[0] - c.bmin[0], dy = c.bmax[1] - c.bmin[1], dz = c.bmax[2] - c.bmin[2];
+  auto area = [&](const double* lo, const double* hi) -> double {
+    double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
     double a = (dx * dy + dy * dz + dz * dx) * 2;
     return std::isfinite(a) ? a : std::numeric_limits<double>::max();
   };
+
   std::vector<DNode<R>> dn;
-  dn.reserve((size_t)std::max(1, nn / W + 16));
-  auto set_box = [&](DNode<R>& d, int c, const rtc_bvh_node& b) {
-    for (int a = 0; a < 3; a++) {
-      d.lo[a][c] = round_down<R>(b.bmin[a]);
-      d.hi[a][c] = round_up<R>(b.bmax[a]);
+  std::vector<CNode> qn;
+  std::vector<uint32_t> unbounded;
+  if constexpr (std::is_same<R, double>::value) {
+    // ---- f64 mode: slot == left-first leaf order (the reference's tie-break key); W-wide uncompressed nodes ----
+    for (int32_t s2 = 0; s2 < n; s2++) {
+      leaf_slot[dfs_leaves[s2]] = s2;
+      slot_prim[s2] = nodes[dfs_leaves[s2]].prim;
     }
-  };
-  auto set_empty = [&](DNode<R>& d, int c) {
-    for (int a = 0; a < 3; a++) {
-      d.lo[a][c] = std::numeric_limits<R>::infinity();
-      d.hi[a][c] = -std::numeric_limits<R>::infinity();
+    // Collapse the binary tree into W-wide nodes. A wide node starts from the two children of a binary node and
+    // repeatedly replaces its largest-area inner child by that child's two children (in place, so the
+    // left-to-right order is kept) until it has W children or only leaves.
+    constexpr int W = Width<R>::value;
+    dn.reserve((size_t)std::max(1, nn / W + 16));
+    auto set_box = [&](DNode<R>& d, int c, const rtc_bvh_node& b) {
+      for (int a = 0; a < 3; a++) {
+        d.lo[a][c] = round_down<R>(b.bmin[a]);
+        d.hi[a][c] = round_up<R>(b.bmax[a]);
+      }
+    };
+    auto set_empty = [&](DNode<R>& d, int c) {
+      for (int a = 0; a < 3; a++) {
+        d.lo[a][c] = std::numeric_limits<R>::infinity();
+        d.hi[a][c] = -std::numeric_limits<R>::infinity();
+      }
+      d.child[c] = REF_EMPTY;
+    };
+    struct Work {
+      int32_t bnode, parent, pslot, stack_use;
+    };
+    std::vector<Work> work;
+    int32_t max_stack = 0;
+    if (nodes[ctx->root].prim >= 0) {
+      dn.emplace_back();
+      std::memset(&dn[0], 0, sizeof(DNode<R>));
+      set_box(dn[0], 0, nodes[ctx->root]);
+      dn[0].child[0] = leaf_ref(ctx->root);
+      for (int c = 1; c < W; c++) set_empty(dn[0], c);
+    } else {
+      work.push_back({ctx->root, -1, 0, 0});
+      while (!work.empty()) {
+        Work wk = work.back();
+        work.pop_back();
+        int32_t kids[W];
+        int nk = 2;
+        kids[0] = nodes[wk.bnode].left;
+        kids[1] = nodes[wk.bnode].right;
+        while (nk < W) {
+          int best = -1;
+          double best_a = -1;
+          for (int c = 0; c < nk; c++)
+            if (nodes[kids[c]].prim < 0) {
+              double a = area(nodes[kids[c]].bmin, nodes[kids[c]].bmax);
+              if (a > best_a) {
+                best_a = a;
+                best = c;
+              }
+            }
+          if (best < 0) break;
+          int32_t e = kids[best];
+          for (int c = nk; c > best + 1; c--) kids[c] = kids[c - 1];
+          kids[best] = nodes[e].left;
+          kids[best + 1] = nodes[e].right;
+          nk++;
+        }
+        const int32_t me = (int32_t)dn.size();
+        dn.emplace_back();
+        std::memset(&dn[me], 0, sizeof(DNode<R>));
+        if (wk.parent >= 0) dn[wk.parent].child[wk.pslot] = (uint32_t)me;
+        const int32_t use = wk.stack_use + (nk - 1);
+        max_stack = std::max(max_stack, use);
+        for (int c = 0; c < W; c++) {
+          if (c >= nk) {
+            set_empty(dn[me], c);
+            continue;
+          }
+          set_box(dn[me], c, nodes[kids[c]]);
+          dn[me].child[c] = nodes[kids[c]].prim >= 0 ? leaf_ref(kids[c]) : REF_EMPTY;  // inner: patched on emission
+        }
+        for (int c = nk - 1; c >= 0; c--)  // left child emitted next: depth-first layout
+          if (nodes[kids[c]].prim < 0) work.push_back({kids[c], me, c, use});
+      }
     }
-    d.child[c] = REF_EMPTY;
-  };
-  struct Work {
-    int32_t bnode;      // binary node this wide node stands for
-    int32_t parent;     // wide parent index (-1 for the root)
-    int32_t pslot;      // child slot in the parent
-    int32_t stack_use;  // stack entries pending above this node
-  };
-  std::vector<Work> work;
-  int32_t max_stack = 0;
-  if (nodes[ctx->root].prim >= 0) {
-    dn.emplace_back();
-    std::memset(&dn[0], 0, sizeof(DNode<R>));
-    set_box(dn[0], 0, nodes[ctx->root]);
-    dn[0].child[0] = leaf_ref(ctx->root);
-    for (int c = 1; c < W; c++) set_empty(dn[0], c);
+    ctx->root_node = 0;
+    if (max_stack + 2 > kTraceStack)
+      return fail(ctx, RTC_ERR_UNSUPPORTED, "BVH needs " + std::to_string(max_stack) + " traversal stack entries, limit is " + std::to_string(kTraceStack - 2));
+    ctx->bvh_depth = max_stack;
   } else {
-    work.push_back({ctx->root, -1, 0, 0});
-    while (!work.empty()) {
-      Work wk = work.back();
-      work.pop_back();
-      int32_t kids[W];
-      int nk = 2;
-      kids[0] = nodes[wk.bnode].left;
-      kids[1] = nodes[wk.bnode].right;
-      while (nk < W) {
-        int best = -1;
-        double best_a = -1;
-        for (int c = 0; c < nk; c++)
-          if (nodes[kids[c]].prim < 0) {
-            double a = area(kids[c]);
-            if (a > best_a) {
-              best_a = a;
-              best = c;
+    // ---- f32 mode: quantised 8-wide tree over the bounded primitives; unbounded ones (planes) in a side list ----
+    // fbox = union of the finite leaf boxes below a binary node, nf = their number (post-order over the tree)
+    std::vector<double> fmin((size_t)nn * 3, std::numeric_limits<double>::infinity()), fmax((size_t)nn * 3, -std::numeric_limits<double>::infinity());
+    std::vector<int32_t> nf(nn, 0);
+    {
+      std::vector<std::pair<int32_t, int>> st;
+      st.push_back({ctx->root, 0});
+      while (!st.empty()) {
+        auto& top = st.back();
+        int32_t i = top.first;
+        const rtc_bvh_node& nd = nodes[i];
+        if (nd.prim >= 0) {
+          bool fin = true;
+          for (int a = 0; a < 3; a++) fin = fin && std::isfinite(nd.bmin[a]) && std::isfinite(nd.bmax[a]);
+          if (fin) {
+            nf[i] = 1;
+            for (int a = 0; a < 3; a++) {
+              fmin[(size_t)i * 3 + a] = nd.bmin[a];
+              fmax[(size_t)i * 3 + a] = nd.bmax[a];
             }
           }
-        if (best < 0) break;
-        int32_t e = kids[best];
-        for (int c = nk; c > best + 1; c--) kids[c] = kids[c - 1];
-        kids[best] = nodes[e].left;
-        kids[best + 1] = nodes[e].right;
-        nk++;
-      }
-      const int32_t me = (int32_t)dn.size();
-      dn.emplace_back();
-      std::memset(&dn[me], 0, sizeof(DNode<R>));
-      if (wk.parent >= 0) dn[wk.parent].child[wk.pslot] = (uint32_t)me;
-      const int32_t use = wk.stack_use + (nk - 1);
-      max_stack = std::max(max_stack, use);
-      for (int c = 0; c < W; c++) {
-        if (c >= nk) {
-          set_empty(dn[me], c);
-          continue;
+          st.pop_back();
+        } else if (top.second == 0) {
+          top.second = 1;
+          st.push_back({nd.right, 0});
+          st.push_back({nd.left, 0});
+        } else {
+          nf[i] = nf[nd.left] + nf[nd.right];
+          for (int a = 0; a < 3; a++) {
+            fmin[(size_t)i * 3 + a] = std::min(fmin[(size_t)nd.left * 3 + a], fmin[(size_t)nd.right * 3 + a]);
+            fmax[(size_t)i * 3 + a] = std::max(fmax[(size_t)nd.left * 3 + a], fmax[(size_t)nd.right * 3 + a]);
+          }
+          st.pop_back();
         }
-        set_box(dn[me], c, nodes[kids[c]]);
-        if (nodes[kids[c]].prim >= 0)
-          dn[me].child[c] = leaf_ref(kids[c]);
-        else
-          dn[me].child[c] = REF_EMPTY;  // patched when the child node is emitted
       }
-      for (int c = nk - 1; c >= 0; c--)  // left child emitted next: depth-first layout
-        if (nodes[kids[c]].prim < 0) work.push_back({kids[c], me, c, use});
     }
+    // a binary node with bounded leaves on one side only is transparent
+    auto resolve = [&](int32_t i) -> int32_t {
+      while (nodes[i].prim < 0) {
+        int32_t l = nodes[i].left, r = nodes[i].right;
+        if (nf[l] == 0) i = r;
+        else if (nf[r] == 0) i = l;
+        else break;
+      }
+      return i;
+    };
+    const int32_t n_bounded = nf[ctx->root];
+    int32_t next_slot = 0;
+    int32_t max_depth = 0;
+    if (n_bounded > 0) {
+      struct QWork {
+        int32_t bnode;   // resolved binary node (inner with two bounded sides, or the single bounded leaf for the root case)
+        int32_t depth;
+      };
+      std::vector<QWork> queue;  // index in this vector == CNode index (breadth-first emission)
+      queue.reserve((size_t)n_bounded / 3 + 16);
+      queue.push_back({resolve(ctx->root), 1});
+      qn.reserve((size_t)n_bounded / 3 + 16);
+      for (size_t qi = 0; qi < queue.size(); qi++) {
+        const QWork wk = queue[qi];
+        max_depth = std::max(max_depth, wk.depth);
+        int32_t kids[8];
+        int nk = 0;
+        if (nodes[wk.bnode].prim >= 0) {
+          kids[nk++] = wk.bnode;  // tree of a single bounded primitive
+        } else {
+          kids[nk++] = resolve(nodes[wk.bnode].left);
+          kids[nk++] = resolve(nodes[wk.bnode].right);
+          while (nk < 8) {
+            int best = -1;
+            double best_a = -1;
+            for (int c = 0; c < nk; c++)
+              if (nodes[kids[c]].prim < 0) {
+                double a = area(&fmin[(size_t)kids[c] * 3], &fmax[(size_t)kids[c] * 3]);
+                if (a > best_a) {
+                  best_a = a;
+                  best = c;
+                }
+              }
+            if (best < 0) break;
+            int32_t e = kids[best];
+            kids[best] = resolve(nodes[e].left);
+            kids[nk++] = resolve(nodes[e].right);
+          }
+        }
+        // node box, grid origin and per-axis power-of-two step
+        double lo[3], hi[3];
+        for (int a = 0; a < 3; a++) {
+          lo[a] = std::numeric_limits<double>::infinity();
+          hi[a] = -std::numeric_limits<double>::infinity();
+          for (int c = 0; c < nk; c++) {
+            lo[a] = std::min(lo[a], fmin[(size_t)kids[c] * 3 + a]);
+            hi[a] = std::max(hi[a], fmax[(size_t)kids[c] * 3 + a]);
+          }
+        }
+        CNode cn;
+        std::memset(&cn, 0, sizeof(cn));
+        float p[3];
+        int ex[3];
+        double step[3];
+        for (int a = 0; a < 3; a++) {
+          // grid: origin one step below the box minimum (so the one-step padding of the children never clamps at 0),
+          // step = smallest power of two that spans the box in 250 steps
+          double ext = hi[a] - lo[a];
+          int e = ext > 0 ? (int)std::ceil(std::log2(ext / 250.0)) : -100;
+          e = std::min(std::max(e, -120), 120);
+          while (std::ldexp(1.0, e) * 250.0 < ext) e++;
+          p[a] = round_down<float>(lo[a] - std::ldexp(1.0, e));
+          while (std::ldexp(1.0, e) * 253.0 < hi[a] - (double)p[a]) {
+            e++;
+            p[a] = round_down<float>(lo[a] - std::ldexp(1.0, e));
+          }
+          ex[a] = e;
+          step[a] = std::ldexp(1.0, e);
+        }
+        cn.px = p[0];
+        cn.py = p[1];
+        cn.pz = p[2];
+        // slot assignment: child i goes to the free slot whose octant signs best match its offset from the centre
+        int slot_of[8];
+        {
+          double ctr[3];
+          for (int a = 0; a < 3; a++) ctr[a] = 0.5 * (lo[a] + hi[a]);
+          double cost[8][8];
+          for (int c = 0; c < nk; c++)
+            for (int s2 = 0; s2 < 8; s2++) {
+              double v = 0;
+              for (int a = 0; a < 3; a++) {
+                double off = 0.5 * (fmin[(size_t)kids[c] * 3 + a] + fmax[(size_t)kids[c] * 3 + a]) - ctr[a];
+                v += ((s2 >> a) & 1) ? off : -off;
+              }
+              cost[c][s2] = v;
+            }
+          bool cu[8] = {false, false, false, false, false, false, false, false}, su[8] = {false, false, false, false, false, false, false, false};
+          for (int it = 0; it < nk; it++) {
+            int bc = -1, bs = -1;
+            double bv = -std::numeric_limits<double>::infinity();
+            for (int c = 0; c < nk; c++)
+              if (!cu[c])
+                for (int s2 = 0; s2 < 8; s2++)
+                  if (!su[s2] && cost[c][s2] > bv) {
+                    bv = cost[c][s2];
+                    bc = c;
+                    bs = s2;
+                  }
+            cu[bc] = true;
+            su[bs] = true;
+            slot_of[bc] = bs;
+          }
+        }
+        int child_in_slot[8];
+        for (int s2 = 0; s2 < 8; s2++) child_in_slot[s2] = -1;
+        for (int c = 0; c < nk; c++) child_in_slot[slot_of[c]] = c;
+        uint32_t imask = 0, lmask = 0;
+        cn.child_base = (uint32_t)queue.size();
+        cn.prim_base = (uint32_t)next_slot;
+        uint8_t qb[6][8];
+        std::memset(qb, 0, sizeof(qb));
+        for (int s2 = 0; s2 < 8; s2++) {
+          int c = child_in_slot[s2];
+          if (c < 0) {
+            for (int a = 0; a < 3; a++) {  // empty slot: inverted box, never hit
+              qb[a][s2] = 255;
+              qb[3 + a][s2] = 0;
+            }
+            continue;
+          }
+          int32_t k = kids[c];
+          for (int a = 0; a < 3; a++) {
+            double ql = std::floor((fmin[(size_t)k * 3 + a] - (double)p[a]) / step[a]) - 1.0;
+            double qh = std::ceil((fmax[(size_t)k * 3 + a] - (double)p[a]) / step[a]) + 1.0;
+            qb[a][s2] = (uint8_t)std::min(255.0, std::max(0.0, ql));
+            qb[3 + a][s2] = (uint8_t)std::min(255.0, std::max(0.0, qh));
+          }
+          if (nodes[k].prim >= 0) {
+            lmask |= 1u << s2;
+            leaf_slot[k] = next_slot;
+            slot_prim[next_slot] = nodes[k].prim;
+            next_slot++;
+          } else {
+            imask |= 1u << s2;
+            queue.push_back({k, wk.depth + 1});
+          }
+        }
+        cn.e_imask = (uint32_t)(ex[0] + 127) | ((uint32_t)(ex[1] + 127) << 8) | ((uint32_t)(ex[2] + 127) << 16) | (imask << 24);
+        cn.lmask = lmask;
+        for (int r = 0; r < 6; r++)
+          for (int s2 = 0; s2 < 8; s2++) cn.q[r * 2 + (s2 >> 2)] |= (uint32_t)qb[r][s2] << (8 * (s2 & 3));
+        qn.push_back(cn);
+      }
+    }
+    if (max_depth + 1 > kQStack)
+      return fail(ctx, RTC_ERR_UNSUPPORTED, "8-wide BVH depth " + std::to_string(max_depth) + " exceeds the traversal stack (" + std::to_string(kQStack - 1) + ")");
+    ctx->bvh_depth = max_depth;
+    // unbounded primitives keep their left-first order, after the bounded ones
+    for (int32_t li = 0; li < n; li++) {
+      int32_t node = dfs_leaves[li];
+      if (leaf_slot[node] >= 0) continue;
+      leaf_slot[node] = next_slot;
+      slot_prim[next_slot] = nodes[node].prim;
+      next_slot++;
+      unbounded.push_back(leaf_ref(node));
+    }
+    ctx->root_node = 0;
   }
-  ctx->root_node = 0;
-  if (max_stack + 2 > kTraceStack)
-    return fail(ctx, RTC_ERR_UNSUPPORTED, "BVH needs " + std::to_string(max_stack) + " traversal stack entries, limit is " + std::to_string(kTraceStack - 2));
-  ctx->bvh_depth = max_stack;
 
   std::vector<DPrim<R>> dp(n);
   std::vector<DMat<R>> dm(n);
@@ -487,6 +703,9 @@ int build_device_scene(rtc_ctx* ctx) {
     return bytes ? cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
   };
   CU(up(&ctx->d_nodes, dn.data(), dn.size() * sizeof(DNode<R>)));
+  if (!qn.empty()) CU(up(&ctx->d_qnodes, qn.data(), qn.size() * sizeof(CNode)));
+  if (!unbounded.empty()) CU(up((void**)&ctx->d_unbounded, unbounded.data(), unbounded.size() * sizeof(uint32_t)));
+  ctx->n_unbounded = (int32_t)unbounded.size();
   CU(up(&ctx->d_prims, dp.data(), dp.size() * sizeof(DPrim<R>)));
   CU(up(&ctx->d_mats, dm.data(), dm.size() * sizeof(DMat<R>)));
   CU(up(&ctx->d_xforms, dx.data(), dx.size() * sizeof(DXform<R>)));

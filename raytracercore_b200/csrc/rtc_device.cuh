@@ -578,7 +578,10 @@ __device__ __forceinline__ void test_leaf(const SceneView<R>& sc, uint32_t ref, 
     bool take = t < best.t;
     if (!take && t == best.t && best.ref != 0xFFFFFFFFu) {
       uint32_t bslot = best.ref & REF_SLOT_MASK;
-      take = (leaf_near < best.near_) || (leaf_near == best.near_ && slot < bslot);
+      if constexpr (Num<R>::is_f64)
+        take = (leaf_near < best.near_) || (leaf_near == best.near_ && slot < bslot);
+      else
+        take = slot < bslot;  // f32 mode: exact-distance ties go to the lower slot (the box near is not tracked)
     }
     if (take) {
       best.t = t;
@@ -657,6 +660,9 @@ constexpr int kStreamThreads = 256;
 #endif
 #ifndef RTC_TRACE_MIN_BLOCKS
 #define RTC_TRACE_MIN_BLOCKS 6
+#endif
+#ifndef RTC_Q8_PRMT
+#define RTC_Q8_PRMT 0
 #endif
 #ifndef RTC_PREFETCH
 #define RTC_PREFETCH 0
@@ -908,6 +914,219 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
     if (active && cur == kNone) {
       active = false;
       finished = true;
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&pv.ctl->nodes_visited, (unsigned long long)n_nodes);
+    atomicAdd(&pv.ctl->prims_tested, (unsigned long long)n_prims);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// trace, f32 production mode: the same warp-synchronous scheduler over the quantised 8-wide tree (CNode).
+//   node step: pop the highest-priority pending child of the current inner group, fetch its node with
+//              2 x LDG.256 + 1 x LDG.128, decode the 8 child boxes (one PRMT + one FFMA per bound: byte q becomes the
+//              float 2^23 + q, the 2^23 is folded into the FMA addend) and intersect them; the hits form one inner group
+//              and one leaf group, addressed implicitly (base + popcount), so at most ONE stack entry is pushed;
+//   leaf step: pop the highest-priority pending leaf of the leaf group and test its primitive.
+// The stack lives in shared memory as [entry][thread] (conflict-free for any per-lane depth).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+__device__ __forceinline__ float qbyte(uint32_t w, int k) {  // float(2^23 + byte k of w)
+#if RTC_Q8_PRMT
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)k));
+#else
+  // dp4a(w, 1 << 8k, 2^23 as float bits) = byte k + 0x4B000000: one IDP.4A on the FMA-heavy pipe instead of a PRMT on the
+  // (half-rate, saturated) ALU pipe
+  return __uint_as_float(__dp4a(w, 1u << (8 * k), 0x4B000000u));
+#endif
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(SceneView<float> sc, PathView<float> pv, int q, int prev,
+                                                                             int cur_buf, int identity_queue) {
+  using R = float;
+  __shared__ uint2 s_stack[kQStack][kTraceThreads];
+  const uint32_t count = pv.ctl->count[q];
+  const uint32_t* queue = pv.queue[q];
+  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t n_nodes = 0, n_prims = 0;
+  bool active = false, finished = false, exhausted = false;
+  uint32_t path = 0;
+  V3<R> o = mk3(0.f, 0.f, 0.f), d = o, inv = o;
+  uint32_t octinv = 0;
+  Skip<R> sk;
+  sk.slot = REF_SLOT_MASK + 1;
+  sk.inside = false;
+  sk.hpos = sk.hnrm = sk.spos = nullptr;
+  Best<R> best;
+  best.t = Num<R>::inf();
+  best.near_ = 0;
+  best.ref = kNone;
+  best.which = 0;
+  int sp = 0;
+  // current groups: inner (igx = child_base, igy = hits << 8 | imask) and leaf (lgx = prim_base, lgy = hits << 8 | lmask);
+  // hit bits are stored at position slot ^ octinv so that the highest set bit is the child to visit first
+  uint32_t igx = 0, igy = 0, lgx = 0, lgy = 0;
+
+  for (;;) {
+    const unsigned m_idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if (m_idle == 0xFFFFFFFFu || (!exhausted && __popc(m_idle) > 32 - kRefill)) {
+      // ---- refill ------------------------------------------------------------------------------------------
+      if (finished) {
+        if (best.ref == kNone) {
+          R w;
+          set_code(w, HIT_MISS);
+          st4(&pv.hpos[cur_buf][path], R(0), R(0), R(0), R(0));
+          st4(&pv.hnrm[cur_buf][path], R(0), R(0), R(0), w);
+        } else {
+          Cand<R> c[2];
+          prim_hits<R, true>(sc, best.ref, o, d, c);
+          const Cand<R>& h = c[best.which];
+          const bool inside = h.inside ^ ((best.ref & REF_INVERT) != 0);
+          R w;
+          set_code(w, (best.ref & REF_SLOT_MASK) | (inside ? HIT_INSIDE : 0u));
+          st4(&pv.hpos[cur_buf][path], h.pos.x, h.pos.y, h.pos.z, h.t);
+          st4(&pv.hnrm[cur_buf][path], h.normal.x, h.normal.y, h.normal.z, w);
+        }
+        finished = false;
+      }
+      if (exhausted) {
+        if (m_idle == 0xFFFFFFFFu) break;
+        continue;
+      }
+      uint32_t base = 0;
+      const int leader = __ffs(m_idle) - 1;
+      if (lane == leader) base = atomicAdd(&pv.ctl->work_trace, (uint32_t)__popc(m_idle));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      bool got = true;
+      if (!active) {
+        const uint32_t idx = base + __popc(m_idle & lt_mask);
+        got = idx < count;
+        if (got) {
+          path = identity_queue ? idx : queue[idx];
+          V4<R> dv = ld4(&pv.dir[path]);
+          V4<R> op = ld4(&pv.hpos[prev][path]);
+          const uint32_t code = code_of(pv.hnrm[prev][path].w);
+          o = xyz(op);
+          d = xyz(dv);
+          inv = mk3(clamped_rcp(d.x), clamped_rcp(d.y), clamped_rcp(d.z));
+          const uint32_t oct = (rsignbit(d.x) ? 1u : 0u) | (rsignbit(d.y) ? 2u : 0u) | (rsignbit(d.z) ? 4u : 0u);
+          octinv = 7u ^ oct;
+          sk.slot = (code == HIT_MISS) ? (REF_SLOT_MASK + 1) : (code & REF_SLOT_MASK);
+          sk.inside = (code & HIT_INSIDE) != 0;
+          sk.hpos = &pv.hpos[prev][path];
+          sk.hnrm = &pv.hnrm[prev][path];
+          sk.spos = pv.skip_pos ? &pv.skip_pos[path] : nullptr;
+          best.t = Num<R>::inf();
+          best.near_ = 0;
+          best.ref = kNone;
+          best.which = 0;
+          sp = 0;
+          // primitives without a finite box (planes) are tested up front, in leaf order
+          for (int i = 0; i < sc.n_unbounded; i++) {
+            if (COUNT) n_prims++;
+            test_leaf<R>(sc, sc.unbounded[i], -Num<R>::inf(), o, d, sk, best);
+          }
+          // virtual root group: one inner child in slot 0 = node 0
+          igx = 0;
+          igy = sc.qnodes ? (((1u << (0u ^ octinv)) << 8) | 1u) : 0u;
+          lgx = 0;
+          lgy = 0;
+          active = true;
+        }
+      }
+      exhausted = !__all_sync(0xFFFFFFFFu, got);
+      continue;
+    }
+
+    const bool want_leaf = active && (lgy >> 8) != 0;
+    const bool want_node = active && !want_leaf && (igy >> 8) != 0;
+    const unsigned m_leaf = __ballot_sync(0xFFFFFFFFu, want_leaf);
+    const unsigned m_node = __ballot_sync(0xFFFFFFFFu, want_node);
+    if (__popc(m_node) >= __popc(m_leaf) && m_node) {
+      // ---- node step ---------------------------------------------------------------------------------------
+      if (want_node) {
+        const uint32_t hits = igy >> 8;
+        const uint32_t b = 31u - (uint32_t)__clz((int)hits);
+        const uint32_t s = b ^ octinv;
+        const uint32_t imask_g = igy & 0xFFu;
+        const uint32_t node = igx + (uint32_t)__popc(imask_g & ((1u << s) - 1u));
+        igy &= ~(0x100u << b);
+        if ((igy >> 8) != 0) {  // siblings still pending: the group goes to the stack
+          s_stack[sp][tid] = make_uint2(igx, igy);
+          sp++;
+        }
+        const CNode* np = sc.qnodes + node;
+        uint32_t w0[8], w1[8];
+        ldg256(np, w0);
+        ldg256(reinterpret_cast<const char*>(np) + 32, w1);
+        const uint4 w2 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(np) + 64));
+        if (COUNT) n_nodes++;
+        const uint32_t em = w0[3];
+        const float sx = __uint_as_float((em & 0xFFu) << 23), sy = __uint_as_float(((em >> 8) & 0xFFu) << 23),
+                    sz = __uint_as_float(((em >> 16) & 0xFFu) << 23);
+        const uint32_t imask = em >> 24, lmask = w0[6] & 0xFFu;
+        // t = (p + q * step - o) * inv = q * (step * inv) + (p - o) * inv ; q enters as 2^23 + q, so the addend carries
+        // -2^23 * step * inv (its rounding is half a grid step: the builder pads every box by one step)
+        const float ax = sx * inv.x, ay = sy * inv.y, az = sz * inv.z;
+        const float bx = fmaf(-8388608.0f, ax, (__uint_as_float(w0[0]) - o.x) * inv.x);
+        const float by = fmaf(-8388608.0f, ay, (__uint_as_float(w0[1]) - o.y) * inv.y);
+        const float bz = fmaf(-8388608.0f, az, (__uint_as_float(w0[2]) - o.z) * inv.z);
+        // near / far byte rows by direction sign: w1 = {lox0,lox1,loy0,loy1,loz0,loz1,hix0,hix1}, w2 = {hiy0,hiy1,hiz0,hiz1}
+        const bool nx_ = inv.x < 0.0f, ny_ = inv.y < 0.0f, nz_ = inv.z < 0.0f;
+        const uint32_t nxw[2] = {nx_ ? w1[6] : w1[0], nx_ ? w1[7] : w1[1]}, fxw[2] = {nx_ ? w1[0] : w1[6], nx_ ? w1[1] : w1[7]};
+        const uint32_t nyw[2] = {ny_ ? w2.x : w1[2], ny_ ? w2.y : w1[3]}, fyw[2] = {ny_ ? w1[2] : w2.x, ny_ ? w1[3] : w2.y};
+        const uint32_t nzw[2] = {nz_ ? w2.z : w1[4], nz_ ? w2.w : w1[5]}, fzw[2] = {nz_ ? w1[4] : w2.z, nz_ ? w1[5] : w2.w};
+        uint32_t hitbits = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int wi = c >> 2, k = c & 3;
+          const float tnx = fmaf(qbyte(nxw[wi], k), ax, bx), tny = fmaf(qbyte(nyw[wi], k), ay, by), tnz = fmaf(qbyte(nzw[wi], k), az, bz);
+          const float tfx = fmaf(qbyte(fxw[wi], k), ax, bx), tfy = fmaf(qbyte(fyw[wi], k), ay, by), tfz = fmaf(qbyte(fzw[wi], k), az, bz);
+          const float nr = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.0f);
+          const float fr = fminf(fminf(fminf(tfx, tfy), tfz), best.t);
+          hitbits |= (nr <= fr) ? (1u << c) : 0u;
+        }
+        // slot order -> visit order: bit s moves to position s ^ octinv (three conditional swaps)
+        uint32_t ih = hitbits & imask, lh = hitbits & lmask;
+        uint32_t hb = ih | (lh << 8);
+        if (octinv & 4u) hb = ((hb & 0x0F0Fu) << 4) | ((hb >> 4) & 0x0F0Fu);
+        if (octinv & 2u) hb = ((hb & 0x3333u) << 2) | ((hb >> 2) & 0x3333u);
+        if (octinv & 1u) hb = ((hb & 0x5555u) << 1) | ((hb >> 1) & 0x5555u);
+        igx = w0[4];
+        igy = ((hb & 0xFFu) << 8) | imask;
+        lgx = w0[5];
+        lgy = (hb & 0xFF00u) | lmask;
+      }
+    } else {
+      // ---- leaf step ---------------------------------------------------------------------------------------
+      if (want_leaf) {
+        const uint32_t hits = lgy >> 8;
+        const uint32_t b = 31u - (uint32_t)__clz((int)hits);
+        const uint32_t s = b ^ octinv;
+        const uint32_t slot = lgx + (uint32_t)__popc((lgy & 0xFFu) & ((1u << s) - 1u));
+        lgy &= ~(0x100u << b);
+        if (COUNT) n_prims++;
+        test_leaf<R>(sc, __ldg(&sc.prim_ref[slot]), R(0), o, d, sk, best);
+      }
+    }
+    if (active && (lgy >> 8) == 0 && (igy >> 8) == 0) {
+      if (sp > 0) {
+        sp--;
+        const uint2 g = s_stack[sp][tid];
+        igx = g.x;
+        igy = g.y;
+      } else {
+        active = false;
+        finished = true;
+      }
     }
   }
   if (COUNT) {
@@ -1214,7 +1433,10 @@ inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 template <typename R>
 int Kernels<R>::trace_blocks_per_sm() {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<R, false>, kTraceThreads, 0);
+  if constexpr (Num<R>::is_f64)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<R, false>, kTraceThreads, 0);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_q8<false>, kTraceThreads, 0);
   return nb > 0 ? nb : 1;
 }
 
@@ -1238,10 +1460,17 @@ cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, cons
                               bool identity_queue) {
   static int per_sm = trace_blocks_per_sm();
   int grid = cfg.sm_count * per_sm;
-  if (cfg.counters)
-    k_trace<R, true><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
-  else
-    k_trace<R, false><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+  if constexpr (Num<R>::is_f64) {
+    if (cfg.counters)
+      k_trace<R, true><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+    else
+      k_trace<R, false><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+  } else {
+    if (cfg.counters)
+      k_trace_q8<true><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+    else
+      k_trace_q8<false><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+  }
   return cudaGetLastError();
 }
 

@@ -68,6 +68,25 @@ struct alignas(next_pow2((6 * (int)sizeof(R) + 4) * W)) DNodeW {
 template <typename R>
 using DNode = DNodeW<R, Width<R>::value>;
 
+// f32 production mode: 8-wide node with child boxes quantised to 8 bits per bound on a per-node power-of-two grid
+// (after Ylitie, Karras & Laine 2017). 96 B, fetched with two 256-bit loads and one 128-bit load — the trace kernel
+// is bound by L1 wavefronts (one per lane and load instruction for incoherent rays), not by bytes. Inner children are
+// stored contiguously from child_base, the primitives of leaf children contiguously from prim_base, so a child is
+// addressed by base + popcount of the mask bits below its slot. Children sit in the slot whose octant code best
+// matches their offset from the node centre: for a ray with octant `oct`, slot s is visited in order of s ^ (7 ^ oct).
+struct alignas(32) CNode {
+  float px, py, pz;     // grid origin = node box minimum
+  uint32_t e_imask;     // ex | ey << 8 | ez << 16 | imask << 24 : grid step 2^(e-127) per axis, inner-child slot mask
+  uint32_t child_base;  // node index of the first inner child
+  uint32_t prim_base;   // slot of the first leaf child's primitive
+  uint32_t lmask;       // leaf-child slot mask
+  uint32_t pad0;
+  uint32_t q[12];       // qlo x,y,z then qhi x,y,z; 8 bytes (two words) each, byte s = child slot s
+  uint32_t pad1[4];
+};
+static_assert(sizeof(CNode) == 96, "CNode layout");
+constexpr int kQStack = 24;  // shared-memory traversal stack entries per lane for the 8-wide tree
+
 template <typename R>
 struct DPrim {
   V4<R> a, b, c;
@@ -94,6 +113,9 @@ struct SceneView {
   const uint32_t* prim_ref;  // per slot: the leaf reference (kind + flags + slot)
   uint32_t root;           // index of the root inner node
   int32_t n_prims;
+  const CNode* qnodes;     // f32 mode only: the quantised 8-wide tree over the bounded primitives
+  const uint32_t* unbounded;  // f32 mode only: leaf references of primitives with infinite boxes (planes)
+  int32_t n_unbounded;
 };
 
 template <typename R>
