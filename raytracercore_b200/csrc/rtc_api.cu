@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -483,6 +484,81 @@ int build_device_scene(rtc_ctx* ctx) {
       }
       return i;
     };
+    // Optimal collapse (after Ylitie, Karras & Laine 2017, sec. 3): T(m, i) = least total surface area of the wide nodes
+    // needed below binary node m when m's subtree may occupy at most i child slots of its parent wide node. A leaf costs
+    // nothing; an inner node either becomes a wide node itself (its area + its two sides spread over 8 slots) or hands
+    // its slots on to its two sides. Evaluated children-first; cut[m][j] is the left side's share when j slots are split.
+    std::vector<float> T((size_t)nn * 8, 0.0f);
+    std::vector<uint8_t> cut((size_t)nn * 9, 0);
+    {
+      std::vector<std::pair<int32_t, int>> st;
+      st.push_back({ctx->root, 0});
+      while (!st.empty()) {
+        auto& top = st.back();
+        const int32_t i = top.first;
+        const rtc_bvh_node& nd = nodes[i];
+        if (nd.prim >= 0 || nf[i] == 0) {
+          st.pop_back();
+          continue;
+        }
+        if (top.second == 0) {
+          top.second = 1;
+          st.push_back({nd.right, 0});
+          st.push_back({nd.left, 0});
+          continue;
+        }
+        st.pop_back();
+        if (nf[nd.left] == 0 || nf[nd.right] == 0) continue;  // transparent: resolve() skips it
+        const int32_t l = resolve(nd.left), r = resolve(nd.right);
+        const float* Tl = &T[(size_t)l * 8];
+        const float* Tr = &T[(size_t)r * 8];
+        float D[9];
+        for (int j = 2; j <= 8; j++) {
+          float bestv = std::numeric_limits<float>::infinity();
+          int bestk = 1;
+          for (int k = 1; k < j; k++) {
+            const float v = Tl[std::min(k, 7)] + Tr[std::min(j - k, 7)];
+            if (v < bestv) {
+              bestv = v;
+              bestk = k;
+            }
+          }
+          D[j] = bestv;
+          cut[(size_t)i * 9 + j] = (uint8_t)bestk;
+        }
+        float* Ti = &T[(size_t)i * 8];
+        const float as_node = (float)area(&fmin[(size_t)i * 3], &fmax[(size_t)i * 3]) + D[8];
+        Ti[1] = as_node;
+        for (int j = 2; j <= 7; j++) Ti[j] = std::min(as_node, D[j]);
+      }
+    }
+    // fills kids[] with the children of the wide node rooted at binary node m
+    auto gather_children = [&](int32_t m, int32_t* kids, int& nk) {
+      struct It {
+        int32_t node;
+        int slots;
+        bool force_split;
+      };
+      It stack_[32];
+      int sp_ = 0;
+      stack_[sp_++] = {m, 8, true};
+      while (sp_ > 0) {
+        It it = stack_[--sp_];
+        const rtc_bvh_node& nd = nodes[it.node];
+        if (nd.prim >= 0) {
+          kids[nk++] = it.node;
+          continue;
+        }
+        const float* Ti = &T[(size_t)it.node * 8];
+        if (!it.force_split && (it.slots == 1 || Ti[std::min(it.slots, 7)] >= Ti[1])) {
+          kids[nk++] = it.node;  // stays a wide node of its own
+          continue;
+        }
+        const int k = cut[(size_t)it.node * 9 + it.slots];
+        stack_[sp_++] = {resolve(nd.right), it.slots - k, false};
+        stack_[sp_++] = {resolve(nd.left), k, false};
+      }
+    };
     const int32_t n_bounded = nf[ctx->root];
     int32_t next_slot = 0;
     int32_t max_depth = 0;
@@ -503,24 +579,7 @@ int build_device_scene(rtc_ctx* ctx) {
         if (nodes[wk.bnode].prim >= 0) {
           kids[nk++] = wk.bnode;  // tree of a single bounded primitive
         } else {
-          kids[nk++] = resolve(nodes[wk.bnode].left);
-          kids[nk++] = resolve(nodes[wk.bnode].right);
-          while (nk < 8) {
-            int best = -1;
-            double best_a = -1;
-            for (int c = 0; c < nk; c++)
-              if (nodes[kids[c]].prim < 0) {
-                double a = area(&fmin[(size_t)kids[c] * 3], &fmax[(size_t)kids[c] * 3]);
-                if (a > best_a) {
-                  best_a = a;
-                  best = c;
-                }
-              }
-            if (best < 0) break;
-            int32_t e = kids[best];
-            kids[best] = resolve(nodes[e].left);
-            kids[nk++] = resolve(nodes[e].right);
-          }
+          gather_children(wk.bnode, kids, nk);
         }
         // node box, grid origin and per-axis power-of-two step
         double lo[3], hi[3];
@@ -627,6 +686,15 @@ int build_device_scene(rtc_ctx* ctx) {
           for (int s2 = 0; s2 < 8; s2++) cn.q[r * 2 + (s2 >> 2)] |= (uint32_t)qb[r][s2] << (8 * (s2 & 3));
         qn.push_back(cn);
       }
+    }
+    if (std::getenv("RTC_B200_VERBOSE")) {
+      size_t kids_total = 0, leaf_total = 0;
+      for (const CNode& c : qn) {
+        kids_total += __builtin_popcount(c.e_imask >> 24) + __builtin_popcount(c.lmask);
+        leaf_total += __builtin_popcount(c.lmask);
+      }
+      std::fprintf(stderr, "[rtcore_b200] q8 tree: %zu nodes, %.2f children/node (%.2f leaves/node), depth %d, %d bounded prims\n",
+                   qn.size(), qn.empty() ? 0.0 : (double)kids_total / qn.size(), qn.empty() ? 0.0 : (double)leaf_total / qn.size(), max_depth, n_bounded);
     }
     if (max_depth + 1 > kQStack)
       return fail(ctx, RTC_ERR_UNSUPPORTED, "8-wide BVH depth " + std::to_string(max_depth) + " exceeds the traversal stack (" + std::to_string(kQStack - 1) + ")");
