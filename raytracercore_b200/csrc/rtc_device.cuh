@@ -359,9 +359,10 @@ __device__ __forceinline__ int sphere_hits(const SceneView<R>& sc, uint32_t ref,
     R disc = radius * radius - dot3(l, l);
     R c = dot3(off, off) - radius * radius;
     R sq = rsqrt_(disc);  // NaN when the ray misses
-    R q = bp + copysignf(sq, bp);
+    const bool fwd = bp >= 0;  // (-0 counts as forward: q must not cancel)
+    R q = fwd ? bp + sq : bp - sq;
     R other = c / q;
-    if (bp >= 0) {
+    if (fwd) {
       t_far = q;
       t_close = other;
     } else {

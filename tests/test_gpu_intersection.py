@@ -1,0 +1,208 @@
+"""Intersection parity (BASELINE.json north_star, test 1): on fixed ray batches the CUDA closest-hit kernel, called
+through the C ABI, must report the oracle's primitive index and inside flag exactly and t / normal within 1e-5
+relative in f64 mode (1e-4 in f32 mode, where rays whose two nearest candidates coincide within the tolerance are
+counted separately as ambiguous)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import SCENES
+from parity import check_hits, random_rays
+from raytracercore_b200 import HIT_DT, RAY_DT, RTC_F32, RTC_F64, Context, RtcError, Scene
+from raytracercore_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+
+MODES = [(RTC_F64, 1e-5, True), (RTC_F32, 1e-4, False)]
+MIXED = """
+size 64 64
+camera 0 -6 1  0 0 0  0 0 1  50
+twosided true
+diffuse .8 .8 .8
+plane -2 0 0 1
+sphere 0 0 0 1
+twosided false
+sphere 2.5 0 0 .7
+invert true
+sphere -2.5 0 0 .7
+invert false
+twosided true
+pushtransform
+translate 0 2 .5
+rotate 1 1 0 30
+scale 1.5 .5 .75
+sphere 0 0 0 1
+poptransform
+cube 0 -2.5 0  1 1 1  all
+pushtransform
+rotate 0 0 1 20
+translate 3 3 0
+cube 0 0 0  1 2 .5  not +z
+poptransform
+vertex -4 -4 -1.5
+vertex 4 -4 -1.5
+vertex 0 4 -1.5
+tri 0 1 2
+twosided false
+vertex -1 -1 2.5
+vertex 1 -1 2.5
+vertex 0 1 2.5
+tri 3 4 5
+plane 8 0 1 0
+"""
+
+
+def secondary(ora, rays, seed):
+    first = ora.trace_closest(rays)
+    m = first["prim"] >= 0
+    rng = np.random.default_rng(seed)
+    sec = np.zeros(int(m.sum()), RAY_DT)
+    sec["origin"] = first["position"][m]
+    d = rng.normal(size=(len(sec), 3))
+    sec["dir"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    return sec, first[m]
+
+
+def run_parity(sc, rays, lo_hi_secondary=True, bvh="scene"):
+    ora = O.OracleScene(sc)
+    want = ora.trace_closest(rays)
+    sec, skip = secondary(ora, rays, 17)
+    want2 = ora.trace_closest(sec, skip)
+    out = {}
+    for prec, tol, exact in MODES:
+        ctx = Context(0, prec)
+        ctx.upload_scene(sc)
+        if bvh == "scene":
+            ctx.upload_bvh(*sc.bvh())
+        else:
+            ctx.build_bvh()
+        got = ctx.trace_closest(rays)
+        amb = check_hits(got, want, tol, exact, origins=rays["origin"], dirs=rays["dir"])
+        # secondary rays start on a surface: exercises the self-hit rule (Util.RayHitMatches) with a skip hit
+        # in f32 mode the skip hit handed over is the f64 oracle hit, as the host would pass it
+        got2 = ctx.trace_closest(sec, skip)
+        amb2 = check_hits(got2, want2, tol, exact, origins=sec["origin"], dirs=sec["dir"], max_ambiguous_frac=0.01)
+        out[prec] = (amb, amb2)
+        ctx.close()
+    return out
+
+
+@pytest.mark.parametrize("name", ["cornell_bounce.scene", "die.scene"])
+def test_reference_scenes(name):
+    sc = Scene.from_file(os.path.join(SCENES, name))
+    rays = random_rays(np.random.default_rng(1), 1 << 17, -2.6, 2.6, RAY_DT)
+    res = run_parity(sc, rays)
+    assert res[RTC_F64] == (0, 0)
+
+
+def test_mixed_primitives_planes_ellipsoid_one_sided_inverted():
+    sc = Scene.from_string(MIXED)
+    rays = random_rays(np.random.default_rng(2), 1 << 16, -5, 5, RAY_DT)
+    res = run_parity(sc, rays)
+    assert res[RTC_F64] == (0, 0)
+    run_parity(sc, rays[:4096], bvh="built")  # rtc_build_bvh path (boxes rebuilt from the flattened description)
+
+
+def test_camera_rays_through_the_scene():
+    sc = Scene.from_file(os.path.join(SCENES, "cornell_bounce.scene"))
+    sc.override(width=192, height=192, recursion=8)
+    ora = O.OracleScene(sc, seed=5)
+    ys, xs = np.mgrid[0:192, 0:192]
+    xy = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.int32)
+    rays = ora.camera_rays(xy, np.zeros(len(xy), np.uint32))
+    run_parity(sc, rays)
+
+
+@pytest.mark.parametrize("name,n", [("soup", 50000), ("spheres", 20000)])
+def test_synthetic_scenes(name, n):
+    sc = Scene.synthetic(name, n, 0xC3 if name == "soup" else 0xC4, 0.03 if name == "soup" else 0.0)
+    rays = random_rays(np.random.default_rng(3), 1 << 16, -1.2, 1.2, RAY_DT)
+    ora = O.OracleScene(sc)
+    want = ora.trace_closest(rays)
+    sec, skip = secondary(ora, rays, 4)
+    want2 = ora.trace_closest(sec, skip)
+    for prec, tol, exact in MODES:
+        ctx = Context(0, prec)
+        ctx.upload_scene(sc)
+        ctx.upload_bvh(*sc.bvh())
+        # tiny far-away spheres: the normal is (P - C) / r with r ~ 0.01, so f32 coordinates limit it to ~1e-4 / r relative
+        ntol = None if exact or name == "soup" else 2e-3
+        check_hits(ctx.trace_closest(rays), want, tol, exact, origins=rays["origin"], dirs=rays["dir"], normal_tol=ntol)
+        check_hits(ctx.trace_closest(sec, skip), want2, tol, exact, origins=sec["origin"], dirs=sec["dir"], normal_tol=ntol, max_ambiguous_frac=0.01)
+        ctx.close()
+
+
+def test_hand_derived_known_answers_on_device():
+    import json
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+    for entry in kat["scenes"]:
+        sc = Scene.from_string("size 8 8\ncamera 0 0 -5 0 0 0 0 1 0 40\n" + entry["text"])
+        rays = np.zeros(len(entry["cases"]), RAY_DT)
+        for i, c in enumerate(entry["cases"]):
+            rays["origin"][i] = c["origin"]
+            rays["dir"][i] = c["dir"]
+        for prec, tol, _ in MODES:
+            ctx = Context(0, prec)
+            ctx.upload_scene(sc)
+            ctx.upload_bvh(*sc.bvh())
+            got = ctx.trace_closest(rays)
+            for i, c in enumerate(entry["cases"]):
+                w = c["hit"]
+                assert got["prim"][i] == w["prim"], (entry["name"], i, prec, got[i])
+                if w["prim"] >= 0:
+                    assert got["inside"][i] == w["inside"]
+                    assert got["t"][i] == pytest.approx(w["t"], rel=tol)
+                    assert np.allclose(got["normal"][i], w["normal"], atol=tol) and np.allclose(got["position"][i], w["position"], atol=10 * tol)
+            ctx.close()
+
+
+def test_edge_cases_and_errors():
+    sc = Scene.from_string("size 8 8\ncamera 0 0 -5 0 0 0 0 1 0 40\ntwosided true\nsphere 0 0 0 1\n")
+    ctx = Context(0, RTC_F32)
+    with pytest.raises(RtcError) as e:
+        ctx.trace_closest(np.zeros(1, RAY_DT))
+    assert e.value.code == N.RTC_ERR_STATE
+    ctx.upload_scene(sc)
+    with pytest.raises(RtcError):
+        ctx.trace_closest(np.zeros(1, RAY_DT))  # no BVH yet
+    ctx.upload_bvh(*sc.bvh())
+    assert len(ctx.trace_closest(np.zeros(0, RAY_DT))) == 0  # empty batch
+    r = np.zeros(3, RAY_DT)
+    r["origin"] = [[0, 0, -3], [0, 0, -3], [5, 5, 5]]
+    r["dir"] = [[0, 0, 1], [0, 1, 0], [0, 0, 0]]  # hit, miss, degenerate zero direction
+    h = ctx.trace_closest(r)
+    assert h["prim"][0] == 0 and h["prim"][1] == -1 and h["prim"][2] == -1
+    # a broken tree is rejected
+    nodes, n, root = ctx.get_bvh()
+    bad = (N.BvhNode * 1)()
+    bad[0].left, bad[0].right, bad[0].prim = 0, 0, -1
+    with pytest.raises(RtcError):
+        ctx.upload_bvh(bad, 1, 0)
+    ctx.close()
+    # plane-only scene (no bounded primitive at all) and single-triangle scene
+    for text in ("twosided true\nplane 1 0 0 1\n", "twosided true\nvertex 0 0 0\nvertex 1 0 0\nvertex 0 1 0\ntri 0 1 2\n"):
+        sc = Scene.from_string("size 8 8\ncamera 0 0 -5 0 0 0 0 1 0 40\n" + text)
+        ora = O.OracleScene(sc)
+        rays = random_rays(np.random.default_rng(9), 2048, -1, 1, RAY_DT)
+        want = ora.trace_closest(rays)
+        for prec, tol, exact in MODES:
+            c2 = Context(0, prec)
+            c2.upload_scene(sc)
+            c2.upload_bvh(*sc.bvh())
+            check_hits(c2.trace_closest(rays), want, tol, exact, origins=rays["origin"], dirs=rays["dir"])
+            c2.close()
+
+
+def test_batches_larger_than_the_path_pool():
+    sc = Scene.from_file(os.path.join(SCENES, "die.scene"))
+    rays = random_rays(np.random.default_rng(21), 70000, -2.5, 2.5, RAY_DT)
+    ctx = Context(0, RTC_F64)
+    ctx.upload_scene(sc)
+    ctx.upload_bvh(*sc.bvh())
+    a = ctx.trace_closest(rays)
+    ctx.set_option(N.RTC_OPT_MAX_PATHS, 16384)  # forces 5 chunks
+    b = ctx.trace_closest(rays)
+    assert a.tobytes() == b.tobytes()
+    ctx.close()
