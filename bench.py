@@ -280,29 +280,33 @@ def main():
     value = rays_all / (ms_max * 1e-3) / 1e6
 
     # ---------------- end-to-end through the C ABI with host buffers ----------------
+    # One step = what FullRaytracer.Start does per frame with host-resident inputs: the host's prepared scene image
+    # (Scene.Prepare output: device-layout primitives + BVH in pinned host memory) is copied to the device, camera and
+    # parameters are handed over as host structs, the pass is rendered, the per-frame collective runs (N > 1) and the
+    # SampleSet planes are read back into pinned host memory.
     e2e = None
     if not args.no_e2e:
-        d = sc.desc()
-        n_prims = d.n_prims
-        rsz = 8 if prec == RTC_F64 else 4
-        dev_bytes = (max(1, n_prims - 1)) * (128 if rsz == 8 else 64) + n_prims * (12 * rsz + 16 * rsz + 16)
-        h2d = n_prims * (12 + 14) * 8 + n_nodes * 64 + 2 * n_prims  # host arrays handed over every step
+        baked = ctx.bake()
+        h2d = baked.nbytes + 8 * 40  # + rtc_camera / rtc_params structs
         d2h = W * H * (24 + 4 + 4)
         par = sc.params(1)
         cam = sc.camera()
         e2e_steps = max(2, min(args.steps, 4))
+        pin_rgb = torch.empty((H, W, 3), dtype=torch.float64, pin_memory=True)
+        pin_s = torch.empty((H, W), dtype=torch.int32, pin_memory=True)
+        pin_m = torch.empty((H, W), dtype=torch.int32, pin_memory=True)
+        out = (pin_rgb.data_ptr(), pin_s.data_ptr(), pin_m.data_ptr())
 
         def e2e_step(step):
-            ctx.upload_scene(d)
-            ctx.upload_bvh(nodes, n_nodes, root)
+            ctx.upload_baked(baked)
             ctx.set_params(par)
             ctx.set_camera(cam)
             ctx.clear_accum()
             ctx.render((step * world + rank) * spp, spp)
             if world > 1:
                 ctx.reduce_accum(0)
-            if rank == 0 or world == 1:
-                ctx.read_accum()
+            if rank == 0:
+                ctx.read_accum(out)
             else:
                 ctx.sync()
 
@@ -325,7 +329,9 @@ def main():
         else:
             rays2 = float(st2.rays)
         e2e = {"value": rays2 / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": dt / e2e_steps * 1e3, "device_bytes_written_per_step": int(dev_bytes)}
+               "ms_per_step": dt / e2e_steps * 1e3,
+               "what": "per step: H2D of the baked scene image from pinned host memory, camera+params structs, render, "
+                       "reduce (N>1), D2H of the SampleSet planes to pinned host memory; wall clock, max over ranks"}
 
     if rank == 0:
         n_prims = sc.n_prims

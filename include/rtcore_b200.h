@@ -189,6 +189,14 @@ int rtc_upload_bvh(rtc_ctx* ctx, int32_t n_nodes, const rtc_bvh_node* nodes, int
 /* Replacement for BVH.Construct (BVH.cs:50-236): binned-SAH build over the uploaded primitives, leaf boxes
  * exactly as AABB.CreateFromBounded (AABB.cs:20-36); planes are chained above the root. */
 int rtc_build_bvh(rtc_ctx* ctx);
+/* Scene.Prepare caches the accelerator on the host (Scene.cs:39-49); the equivalent here is a host-resident image of
+ * the device layout (pinned memory), made once from the current scene + BVH and re-uploaded with plain H2D copies at
+ * every FullRaytracer.Start(). A baked image belongs to one arithmetic mode. */
+typedef struct rtc_baked rtc_baked;
+int rtc_bake(rtc_ctx* ctx, rtc_baked** out);
+int rtc_upload_baked(rtc_ctx* ctx, const rtc_baked* baked);
+int64_t rtc_baked_bytes(const rtc_baked* baked);
+void rtc_baked_free(rtc_baked* baked);
 /* Read the current tree back in reference shape (for SceneInspector.cs:226-265 and for the parity oracle). */
 int rtc_get_bvh_size(rtc_ctx* ctx, int32_t* n_nodes, int32_t* root);
 int rtc_get_bvh(rtc_ctx* ctx, int32_t capacity, rtc_bvh_node* nodes);

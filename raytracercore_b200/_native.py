@@ -86,6 +86,10 @@ SIGNATURES = {
     "rtc_upload_scene": (C.c_int, [_P, C.POINTER(SceneDesc)]),
     "rtc_upload_bvh": (C.c_int, [_P, C.c_int32, C.POINTER(BvhNode), C.c_int32]),
     "rtc_build_bvh": (C.c_int, [_P]),
+    "rtc_bake": (C.c_int, [_P, C.POINTER(_P)]),
+    "rtc_upload_baked": (C.c_int, [_P, _P]),
+    "rtc_baked_bytes": (C.c_int64, [_P]),
+    "rtc_baked_free": (None, [_P]),
     "rtc_get_bvh_size": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rtc_get_bvh": (C.c_int, [_P, C.c_int32, C.POINTER(BvhNode)]),
     "rtc_set_camera": (C.c_int, [_P, C.POINTER(Camera)]),

@@ -69,6 +69,36 @@ struct TimedLaunch {
 };
 }  // namespace
 
+// Host-resident image of the device scene layout (one pinned buffer + segment table): what Scene.Prepare leaves
+// behind on the host side, uploadable with plain H2D copies.
+struct rtc_baked {
+  enum { S_NODES, S_QNODES, S_UNBOUNDED, S_PRIMS, S_MATS, S_XFORMS, S_AUX, S_PRIM_ID, S_ID_TO_SLOT, S_PRIM_REF, S_COUNT };
+  int precision = RTC_F32;
+  int32_t n_prims = 0, n_unbounded = 0, n_xforms = 0, bvh_depth = 0;
+  uint32_t root_node = 0;
+  size_t off[S_COUNT] = {0}, bytes[S_COUNT] = {0};
+  char* host = nullptr;
+  size_t total = 0;
+  bool pinned = false;
+  ~rtc_baked() {
+    if (host) {
+      if (pinned) cudaFreeHost(host);
+      else std::free(host);
+    }
+  }
+  bool alloc(size_t n) {
+    total = n;
+    if (cudaMallocHost((void**)&host, std::max<size_t>(n, 16)) == cudaSuccess) {
+      pinned = true;
+      return true;
+    }
+    cudaGetLastError();
+    host = (char*)std::malloc(std::max<size_t>(n, 16));
+    pinned = false;
+    return host != nullptr;
+  }
+};
+
 struct rtc_ctx {
   int device = 0;
   int precision = RTC_F32;
@@ -97,6 +127,8 @@ struct rtc_ctx {
   int32_t n_unbounded = 0;
   uint32_t root_node = 0;
   int bvh_depth = 0;
+  size_t seg_cap[rtc_baked::S_COUNT] = {0};  // device capacity per scene segment (buffers are reused across uploads)
+  rtc_baked* baked = nullptr;               // image of the current device scene
 
   // path pool
   int64_t max_paths = 1 << 23;
@@ -164,6 +196,7 @@ void free_scene_device(rtc_ctx* c) {
   free_dev(c->d_qnodes);
   free_dev_t(c->d_unbounded);
   c->n_unbounded = 0;
+  for (size_t& v : c->seg_cap) v = 0;
 }
 
 void free_pool(rtc_ctx* c) {
@@ -293,6 +326,38 @@ R round_up(double x) {
     if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
     return std::nextafterf(f, std::numeric_limits<float>::infinity());
   }
+}
+
+// H2D copy of a baked scene image into (reused) device buffers.
+int upload_baked_image(rtc_ctx* ctx, const rtc_baked* bk) {
+  void** dst[rtc_baked::S_COUNT] = {&ctx->d_nodes, &ctx->d_qnodes, (void**)&ctx->d_unbounded, &ctx->d_prims, &ctx->d_mats,
+                                    &ctx->d_xforms, (void**)&ctx->d_aux, (void**)&ctx->d_prim_id, (void**)&ctx->d_id_to_slot,
+                                    (void**)&ctx->d_prim_ref};
+  for (int i = 0; i < rtc_baked::S_COUNT; i++) {
+    const size_t need = std::max<size_t>(bk->bytes[i], 16);
+    if (ctx->seg_cap[i] < need || !*dst[i]) {
+      if (*dst[i]) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(*dst[i]);
+        *dst[i] = nullptr;
+      }
+      CU(cudaMalloc(dst[i], need));
+      ctx->seg_cap[i] = need;
+    }
+    if (bk->bytes[i]) CU(cudaMemcpyAsync(*dst[i], bk->host + bk->off[i], bk->bytes[i], cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (bk->bytes[rtc_baked::S_QNODES] == 0 && bk->precision == RTC_F32) {
+    // no bounded primitive: the kernel keys on a null qnodes pointer
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_qnodes);
+    ctx->d_qnodes = nullptr;
+    ctx->seg_cap[rtc_baked::S_QNODES] = 0;
+  }
+  ctx->n_unbounded = bk->n_unbounded;
+  ctx->root_node = bk->root_node;
+  ctx->bvh_depth = bk->bvh_depth;
+  if (!bk->pinned) CU(cudaStreamSynchronize(ctx->stream));
+  return RTC_OK;
 }
 
 // Flatten the reference-shaped tree + primitives into the device layout (see rtc_internal.h).
@@ -764,25 +829,34 @@ int build_device_scene(rtc_ctx* ctx) {
     }
   }
 
-  free_scene_device(ctx);
-  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
-    cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
-    if (e != cudaSuccess) return e;
-    return bytes ? cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
-  };
-  CU(up(&ctx->d_nodes, dn.data(), dn.size() * sizeof(DNode<R>)));
-  if (!qn.empty()) CU(up(&ctx->d_qnodes, qn.data(), qn.size() * sizeof(CNode)));
-  if (!unbounded.empty()) CU(up((void**)&ctx->d_unbounded, unbounded.data(), unbounded.size() * sizeof(uint32_t)));
-  ctx->n_unbounded = (int32_t)unbounded.size();
-  CU(up(&ctx->d_prims, dp.data(), dp.size() * sizeof(DPrim<R>)));
-  CU(up(&ctx->d_mats, dm.data(), dm.size() * sizeof(DMat<R>)));
-  CU(up(&ctx->d_xforms, dx.data(), dx.size() * sizeof(DXform<R>)));
-  CU(up((void**)&ctx->d_aux, aux.data(), aux.size() * sizeof(int32_t)));
-  CU(up((void**)&ctx->d_prim_id, prim_id.data(), prim_id.size() * sizeof(int32_t)));
-  CU(up((void**)&ctx->d_id_to_slot, id_to_slot.data(), id_to_slot.size() * sizeof(int32_t)));
-  CU(up((void**)&ctx->d_prim_ref, prim_ref.data(), prim_ref.size() * sizeof(uint32_t)));
-  CU(cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope
-  return RTC_OK;
+  rtc_baked* bk = new rtc_baked();
+  bk->precision = ctx->precision;
+  bk->n_prims = n;
+  bk->n_unbounded = (int32_t)unbounded.size();
+  bk->n_xforms = ctx->n_xforms;
+  bk->bvh_depth = ctx->bvh_depth;
+  bk->root_node = ctx->root_node;
+  const void* src[rtc_baked::S_COUNT] = {dn.data(), qn.data(), unbounded.data(), dp.data(), dm.data(), dx.data(),
+                                         aux.data(), prim_id.data(), id_to_slot.data(), prim_ref.data()};
+  const size_t sz[rtc_baked::S_COUNT] = {dn.size() * sizeof(DNode<R>), qn.size() * sizeof(CNode), unbounded.size() * sizeof(uint32_t),
+                                         dp.size() * sizeof(DPrim<R>), dm.size() * sizeof(DMat<R>), dx.size() * sizeof(DXform<R>),
+                                         aux.size() * sizeof(int32_t), prim_id.size() * sizeof(int32_t),
+                                         id_to_slot.size() * sizeof(int32_t), prim_ref.size() * sizeof(uint32_t)};
+  size_t total = 0;
+  for (int i = 0; i < rtc_baked::S_COUNT; i++) {
+    bk->off[i] = total;
+    bk->bytes[i] = sz[i];
+    total += (sz[i] + 255) & ~(size_t)255;
+  }
+  if (!bk->alloc(total)) {
+    delete bk;
+    return fail(ctx, RTC_ERR_NOMEM, "host allocation for the baked scene failed");
+  }
+  for (int i = 0; i < rtc_baked::S_COUNT; i++)
+    if (sz[i]) std::memcpy(bk->host + bk->off[i], src[i], sz[i]);
+  delete ctx->baked;
+  ctx->baked = bk;
+  return upload_baked_image(ctx, bk);
 }
 
 int ready(rtc_ctx* ctx, bool need_camera) {
@@ -1040,6 +1114,7 @@ void rtc_destroy(rtc_ctx* ctx) {
   drain_timing(ctx);
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
   free_scene_device(ctx);
+  delete ctx->baked;
   free_pool(ctx);
   free_dev_t(ctx->d_ctl);
   free_dev_t(ctx->d_rays);
@@ -1126,7 +1201,7 @@ int rtc_upload_bvh(rtc_ctx* ctx, int32_t n_nodes, const rtc_bvh_node* nodes, int
 
 int rtc_build_bvh(rtc_ctx* ctx) {
   if (!ctx) return RTC_ERR_INVALID;
-  if (!ctx->scene_set) return fail(ctx, RTC_ERR_STATE, "upload the scene before building the BVH");
+  if (!ctx->scene_set || (int32_t)ctx->kind.size() != ctx->n_prims) return fail(ctx, RTC_ERR_STATE, "upload the scene before building the BVH");
   if (ctx->n_prims == 0) return fail(ctx, RTC_ERR_INVALID, "scene has no primitives");
   rtc_scene_desc d;
   d.n_prims = ctx->n_prims;
@@ -1145,9 +1220,66 @@ int rtc_build_bvh(rtc_ctx* ctx) {
   return finish_bvh(ctx);
 }
 
+int rtc_bake(rtc_ctx* ctx, rtc_baked** out) {
+  if (!ctx || !out) return RTC_ERR_INVALID;
+  *out = nullptr;
+  if (!ctx->bvh_set || !ctx->baked) return fail(ctx, RTC_ERR_STATE, "no scene + BVH to bake (rtc_upload_scene, then rtc_upload_bvh or rtc_build_bvh)");
+  cudaSetDevice(ctx->device);
+  rtc_baked* c = new rtc_baked();
+  const rtc_baked* b = ctx->baked;
+  c->precision = b->precision;
+  c->n_prims = b->n_prims;
+  c->n_unbounded = b->n_unbounded;
+  c->n_xforms = b->n_xforms;
+  c->bvh_depth = b->bvh_depth;
+  c->root_node = b->root_node;
+  std::memcpy(c->off, b->off, sizeof(c->off));
+  std::memcpy(c->bytes, b->bytes, sizeof(c->bytes));
+  if (!c->alloc(b->total)) {
+    delete c;
+    return fail(ctx, RTC_ERR_NOMEM, "host allocation for the baked scene failed");
+  }
+  std::memcpy(c->host, b->host, b->total);
+  *out = c;
+  return RTC_OK;
+}
+
+int rtc_upload_baked(rtc_ctx* ctx, const rtc_baked* baked) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!baked) return fail(ctx, RTC_ERR_INVALID, "baked scene is null");
+  if (baked->precision != ctx->precision) return fail(ctx, RTC_ERR_INVALID, "baked scene was made for the other arithmetic mode");
+  cudaSetDevice(ctx->device);
+  int rc = upload_baked_image(ctx, baked);
+  if (rc) return rc;
+  ctx->n_prims = baked->n_prims;
+  ctx->n_xforms = baked->n_xforms;
+  if ((int32_t)ctx->kind.size() != baked->n_prims) {  // no host-side description behind this image
+    ctx->kind.clear();
+    ctx->flags.clear();
+    ctx->geom.clear();
+    ctx->material.clear();
+    ctx->xform.clear();
+    ctx->xforms.clear();
+    ctx->nodes.clear();
+    ctx->root = -1;
+  }
+  ctx->scene_set = true;
+  ctx->bvh_set = true;
+  return RTC_OK;
+}
+
+int64_t rtc_baked_bytes(const rtc_baked* baked) {
+  if (!baked) return 0;
+  int64_t t = 0;
+  for (size_t b : baked->bytes) t += (int64_t)b;
+  return t;
+}
+
+void rtc_baked_free(rtc_baked* baked) { delete baked; }
+
 int rtc_get_bvh_size(rtc_ctx* ctx, int32_t* n_nodes, int32_t* root) {
   if (!ctx || !n_nodes || !root) return RTC_ERR_INVALID;
-  if (!ctx->bvh_set) return fail(ctx, RTC_ERR_STATE, "no BVH");
+  if (!ctx->bvh_set || ctx->nodes.empty()) return fail(ctx, RTC_ERR_STATE, "no host-side BVH (none set, or the scene came from rtc_upload_baked)");
   *n_nodes = (int32_t)ctx->nodes.size();
   *root = ctx->root;
   return RTC_OK;

@@ -16,6 +16,26 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+class Baked:
+    def __init__(self, h):
+        self._h = h
+
+    @property
+    def nbytes(self):
+        return int(N.lib.rtc_baked_bytes(self._h))
+
+    def close(self):
+        if self._h:
+            N.lib.rtc_baked_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One rtc_ctx: one GPU, one caller at a time."""
 
@@ -70,6 +90,15 @@ class Context:
         self._ck(N.lib.rtc_get_bvh(self._h, n.value, nodes))
         return nodes, n.value, root.value
 
+    def bake(self):
+        """Host-resident (pinned) image of the current device scene; re-upload with upload_baked()."""
+        h = C.c_void_p()
+        self._ck(N.lib.rtc_bake(self._h, C.byref(h)))
+        return Baked(h)
+
+    def upload_baked(self, baked):
+        self._ck(N.lib.rtc_upload_baked(self._h, baked._h))
+
     def set_camera(self, cam):
         self._ck(N.lib.rtc_set_camera(self._h, C.byref(cam)))
 
@@ -117,14 +146,18 @@ class Context:
     def clear_accum(self):
         self._ck(N.lib.rtc_clear_accum(self._h))
 
-    def read_accum(self):
-        n = self.width * self.height
-        rgb = np.zeros((self.height, self.width, 3), dtype=np.float64)
-        s = np.zeros((self.height, self.width), dtype=np.uint32)
-        m = np.zeros((self.height, self.width), dtype=np.uint32)
-        assert n > 0
-        self._ck(N.lib.rtc_read_accum(self._h, _ptr(rgb), _ptr(s), _ptr(m)))
-        return rgb, s, m
+    def read_accum(self, out=None):
+        """out: optional (rgb f64 [h,w,3], samples u32 [h,w], misses u32 [h,w]) arrays or raw pointers (e.g. pinned)."""
+        assert self.width * self.height > 0
+        if out is None:
+            rgb = np.zeros((self.height, self.width, 3), dtype=np.float64)
+            s = np.zeros((self.height, self.width), dtype=np.uint32)
+            m = np.zeros((self.height, self.width), dtype=np.uint32)
+            self._ck(N.lib.rtc_read_accum(self._h, _ptr(rgb), _ptr(s), _ptr(m)))
+            return rgb, s, m
+        ptrs = [C.c_void_p(o) if isinstance(o, int) else _ptr(o) for o in out]
+        self._ck(N.lib.rtc_read_accum(self._h, *ptrs))
+        return out
 
     def write_accum(self, rgb, samples, misses):
         rgb = np.ascontiguousarray(rgb, dtype=np.float64)

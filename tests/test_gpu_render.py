@@ -277,3 +277,30 @@ def test_full_size_properties_1m_triangle_scene():
     rgb3, s3, m3 = ctx.read_accum()
     assert np.array_equal(rgb2, rgb3) and np.array_equal(s2, s3) and np.array_equal(m2, m3)  # idempotent + additive
     ctx.close()
+
+
+def test_baked_scene_image_round_trip():
+    """rtc_bake / rtc_upload_baked: the host-resident device image renders exactly like the original hand-over."""
+    sc = cornell(64, 64, 6)
+    for prec in (RTC_F32, RTC_F64):
+        ctx = Context(0, prec)
+        ctx.load(sc, seed=3)
+        ctx.render(0, 2)
+        a = ctx.read_accum()
+        baked = ctx.bake()
+        assert baked.nbytes > 22 * 48
+        ctx2 = Context(0, prec)
+        ctx2.upload_baked(baked)
+        ctx2.set_params(sc.params(3))
+        ctx2.set_camera(sc.camera())
+        ctx2.render(0, 2)
+        b = ctx2.read_accum()
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        other = Context(0, RTC_F64 if prec == RTC_F32 else RTC_F32)
+        with pytest.raises(N.RtcError):
+            other.upload_baked(baked)  # an image belongs to one arithmetic mode
+        with pytest.raises(N.RtcError):
+            ctx2.get_bvh()  # no host-side tree behind a baked image
+        for c in (ctx, ctx2, other):
+            c.close()
+        baked.close()
