@@ -206,3 +206,29 @@ def test_batches_larger_than_the_path_pool():
     b = ctx.trace_closest(rays)
     assert a.tobytes() == b.tobytes()
     ctx.close()
+
+
+def test_vertex_normal_triangles_keep_the_reference_quirks():
+    """`trinormal` (Triangle.cs:46-52,211-219): barycentric weights (u, v, u+v) and, for back-face hits, a reflection
+    about the never-computed face Normal, i.e. NaN. Restated, not fixed."""
+    sc = Scene.from_string("size 8 8\ncamera 0 0 -5 0 0 0 0 1 0 40\ntwosided true\n"
+                           "vertexnormal -1 -1 0  0 0 1\nvertexnormal 1 -1 0  1 0 1\nvertexnormal 0 1 0  0 1 1\ntrinormal 0 1 2\n")
+    rng = np.random.default_rng(5)
+    n = 4000
+    rays = np.zeros(n, RAY_DT)
+    rays["origin"] = np.c_[rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), np.where(np.arange(n) % 2 == 0, 2.0, -2.0)]
+    rays["dir"] = np.c_[np.zeros(n), np.zeros(n), np.where(np.arange(n) % 2 == 0, -1.0, 1.0)]
+    want = O.OracleScene(sc).trace_closest(rays)
+    hit = want["prim"] == 0
+    assert hit.sum() > 500
+    for prec, tol in ((RTC_F64, 1e-12), (RTC_F32, 1e-5)):
+        ctx = Context(0, prec)
+        ctx.upload_scene(sc)
+        ctx.upload_bvh(*sc.bvh())
+        got = ctx.trace_closest(rays)
+        assert np.array_equal(got["prim"], want["prim"]) and np.array_equal(got["inside"], want["inside"])
+        front = hit & (want["inside"] == 0)
+        back = hit & (want["inside"] == 1)
+        assert np.allclose(got["normal"][front], want["normal"][front], atol=tol)
+        assert np.isnan(want["normal"][back]).all() and np.isnan(got["normal"][back]).all()
+        ctx.close()
