@@ -155,6 +155,8 @@ typedef struct rtc_stats {
   double ms[RTC_K_COUNT];         /* CUDA-event time per kernel family (only while timing is enabled)    */
   uint64_t nodes_visited;         /* only with rtc_set_option(RTC_OPT_COUNTERS,1): BVH nodes fetched     */
   uint64_t prims_tested;          /*   "                                          primitive tests        */
+  uint64_t node_steps;            /*   "   warp-level node iterations of the f32 trace scheduler                */
+  uint64_t leaf_steps;            /*   "   warp-level leaf iterations                                           */
 } rtc_stats;
 
 enum {

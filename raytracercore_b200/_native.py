@@ -60,7 +60,8 @@ class DebugRay(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("launches", C.c_uint64 * RTC_K_COUNT),
-                ("ms", C.c_double * RTC_K_COUNT), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64)]
+                ("ms", C.c_double * RTC_K_COUNT), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
+                ("node_steps", C.c_uint64), ("leaf_steps", C.c_uint64)]
 
 
 class Globals(C.Structure):

@@ -1543,6 +1543,8 @@ int rtc_get_stats(rtc_ctx* ctx, rtc_stats* stats) {
   stats->rays += h.rays;
   stats->nodes_visited = h.nodes_visited;
   stats->prims_tested = h.prims_tested;
+  stats->node_steps = h.node_steps;
+  stats->leaf_steps = h.leaf_steps;
   return RTC_OK;
 }
 

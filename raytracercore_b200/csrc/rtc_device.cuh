@@ -718,7 +718,13 @@ __global__ void __launch_bounds__(kStreamThreads) k_camera_rays(CameraView<R> ca
 // node vs leaf is greedy: whichever has more lanes ready runs, the other lanes wait. Leaves are ~1 in 16 steps of a
 // ray, so a plain while-while loop (all lanes reach a leaf before any is tested) leaves ~3/4 of the lanes idle.
 // The per-lane stack holds (node, box near) pairs so stale entries are discarded without fetching the node.
-constexpr int kRefill = 24;
+#ifndef RTC_REFILL
+#define RTC_REFILL 24
+#endif
+#ifndef RTC_LEAF_T
+#define RTC_LEAF_T 8
+#endif
+constexpr int kRefill = RTC_REFILL;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
 template <typename R>
@@ -957,7 +963,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
   const int lane = threadIdx.x & 31;
   const int tid = threadIdx.x;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  uint32_t n_nodes = 0, n_prims = 0;
+  uint32_t n_nodes = 0, n_prims = 0, n_node_steps = 0, n_leaf_steps = 0;
   bool active = false, finished = false, exhausted = false;
   uint32_t path = 0;
   V3<R> o = mk3(0.f, 0.f, 0.f), d = o, inv = o;
@@ -1051,8 +1057,13 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
     const bool want_node = active && !want_leaf && (igy >> 8) != 0;
     const unsigned m_leaf = __ballot_sync(0xFFFFFFFFu, want_leaf);
     const unsigned m_node = __ballot_sync(0xFFFFFFFFu, want_node);
+#if RTC_LEAF_T > 0
+    if (m_node && __popc(m_leaf) < RTC_LEAF_T) {
+#else
     if (__popc(m_node) >= __popc(m_leaf) && m_node) {
+#endif
       // ---- node step ---------------------------------------------------------------------------------------
+      if (COUNT && lane == 0) n_node_steps++;
       if (want_node) {
         const uint32_t hits = igy >> 8;
         const uint32_t b = 31u - (uint32_t)__clz((int)hits);
@@ -1108,6 +1119,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
       }
     } else {
       // ---- leaf step ---------------------------------------------------------------------------------------
+      if (COUNT && lane == 0) n_leaf_steps++;
       if (want_leaf) {
         const uint32_t hits = lgy >> 8;
         const uint32_t b = 31u - (uint32_t)__clz((int)hits);
@@ -1133,6 +1145,10 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
   if (COUNT) {
     atomicAdd(&pv.ctl->nodes_visited, (unsigned long long)n_nodes);
     atomicAdd(&pv.ctl->prims_tested, (unsigned long long)n_prims);
+    if (lane == 0) {
+      atomicAdd(&pv.ctl->node_steps, (unsigned long long)n_node_steps);
+      atomicAdd(&pv.ctl->leaf_steps, (unsigned long long)n_leaf_steps);
+    }
   }
 }
 

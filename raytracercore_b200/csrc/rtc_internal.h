@@ -147,6 +147,7 @@ struct Control {            // device-resident launch control block
   uint32_t pad;
   unsigned long long rays;  // closest-hit queries issued (sum of queue lengths over bounces)
   unsigned long long nodes_visited, prims_tested;  // RTC_OPT_COUNTERS
+  unsigned long long node_steps, leaf_steps;       // RTC_OPT_COUNTERS: warp-level scheduler iterations (f32 kernel)
 };
 
 template <typename R>

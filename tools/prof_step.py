@@ -46,3 +46,6 @@ if st.ms[N.RTC_K_TRACE] > 0:
     print("trace-only Mrays/s: %.1f" % (st.rays / st.ms[N.RTC_K_TRACE] / 1e3))
 if a.counters:
     print("nodes/ray %.1f prims/ray %.2f" % (st.nodes_visited / st.rays, st.prims_tested / st.rays))
+    if st.node_steps:
+        print("lanes per node step %.1f, per leaf step %.1f; warp node steps %d leaf steps %d" % (
+            st.nodes_visited / st.node_steps, st.prims_tested / max(1, st.leaf_steps), st.node_steps, st.leaf_steps))
