@@ -1026,7 +1026,7 @@ int trace_batch(rtc_ctx* ctx, int64_t n, const rtc_ray* rays, const rtc_hit* ski
       CU(Kernels<R>::trace(cfg, sv, pv, 0, 1, 0, true));
     }
     ctx->stats.rays += (uint64_t)m;
-    CU(Kernels<R>::export_hits(cfg, sv, m, pv, 0, ctx->d_hits));
+    CU(Kernels<R>::export_hits(cfg, sv, m, pv, 0, ctx->d_hits, true));
     CU(cudaMemcpyAsync(out + off, ctx->d_hits, sizeof(rtc_hit) * m, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
   }
@@ -1504,7 +1504,7 @@ int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t
       if (!ctx->d_hits) {
         CU(cudaMalloc((void**)&ctx->d_hits, sizeof(rtc_hit) * 1024));
       }
-      CU(Kernels<R>::export_hits(cfg, sv, 1, pv, cur, ctx->d_hits));
+      CU(Kernels<R>::export_hits(cfg, sv, 1, pv, cur, ctx->d_hits, false));
       CU(cudaMemcpyAsync(hits.data(), ctx->d_hits, sizeof(rtc_hit), cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaMemcpyAsync(&type, ctx->d_dbg_type, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       if (sizeof(R) == 8)

@@ -588,10 +588,26 @@ __device__ __forceinline__ void test_leaf(const SceneView<R>& sc, uint32_t ref, 
       best.t = t;
       best.near_ = leaf_near;
       best.ref = ref;
-      best.which = i;
+      best.which = i | (inside ? 2 : 0);
     }
     break;  // :68-70 first acceptable hit of this primitive
   }
+}
+
+// Completes a trace result (distance, slot, inside, which) into the full Hit record (Hit.cs:14-20) by re-evaluating the
+// winning primitive once. Runs in the streaming kernels (k_shade, k_export_hits), not in the traversal loop.
+template <typename R>
+__device__ __forceinline__ void finalize_hit(const SceneView<R>& sc, uint32_t code, const V3<R>& o, const V3<R>& d, V3<R>& pos,
+                                             V3<R>& normal, R& t) {
+  const uint32_t ref = __ldg(&sc.prim_ref[code & REF_SLOT_MASK]);
+  Cand<R> c[2];
+  c[0].t = c[1].t = Num<R>::nan();
+  c[0].pos = c[1].pos = c[0].normal = c[1].normal = mk3(Num<R>::nan(), Num<R>::nan(), Num<R>::nan());
+  prim_hits<R, true>(sc, ref, o, d, c);
+  const Cand<R>& h = c[(code & HIT_SECOND) ? 1 : 0];
+  pos = h.pos;
+  normal = h.normal;
+  t = h.t;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -774,22 +790,11 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
     const unsigned m_idle = __ballot_sync(0xFFFFFFFFu, !active);
     if (m_idle == 0xFFFFFFFFu || (!exhausted && __popc(m_idle) > 32 - kRefill)) {
       // ---- refill ------------------------------------------------------------------------------------------
-      if (finished) {  // Hit record for the shade kernel / next bounce's skip hit
-        if (best.ref == kNone) {
-          R w;
-          set_code(w, HIT_MISS);
-          st4(&pv.hpos[cur_buf][path], R(0), R(0), R(0), R(0));
-          st4(&pv.hnrm[cur_buf][path], R(0), R(0), R(0), w);
-        } else {
-          Cand<R> c[2];
-          prim_hits<R, true>(sc, best.ref, o, d, c);
-          const Cand<R>& h = c[best.which];
-          const bool inside = h.inside ^ ((best.ref & REF_INVERT) != 0);
-          R w;
-          set_code(w, (best.ref & REF_SLOT_MASK) | (inside ? HIT_INSIDE : 0u));
-          st4(&pv.hpos[cur_buf][path], h.pos.x, h.pos.y, h.pos.z, h.t);
-          st4(&pv.hnrm[cur_buf][path], h.normal.x, h.normal.y, h.normal.z, w);
-        }
+      if (finished) {  // (distance, slot | inside | which): position and normal are completed by finalize_hit in k_shade
+        R w;
+        set_code(w, best.ref == kNone ? HIT_MISS : ((best.ref & REF_SLOT_MASK) | (best.which & 2 ? HIT_INSIDE : 0u) | (best.which & 1 ? HIT_SECOND : 0u)));
+        st4(&pv.hpos[cur_buf][path], R(0), R(0), R(0), best.t);
+        st4(&pv.hnrm[cur_buf][path], R(0), R(0), R(0), w);
         finished = false;
       }
       if (exhausted) {
@@ -986,22 +991,11 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
     const unsigned m_idle = __ballot_sync(0xFFFFFFFFu, !active);
     if (m_idle == 0xFFFFFFFFu || (!exhausted && __popc(m_idle) > 32 - kRefill)) {
       // ---- refill ------------------------------------------------------------------------------------------
-      if (finished) {
-        if (best.ref == kNone) {
-          R w;
-          set_code(w, HIT_MISS);
-          st4(&pv.hpos[cur_buf][path], R(0), R(0), R(0), R(0));
-          st4(&pv.hnrm[cur_buf][path], R(0), R(0), R(0), w);
-        } else {
-          Cand<R> c[2];
-          prim_hits<R, true>(sc, best.ref, o, d, c);
-          const Cand<R>& h = c[best.which];
-          const bool inside = h.inside ^ ((best.ref & REF_INVERT) != 0);
-          R w;
-          set_code(w, (best.ref & REF_SLOT_MASK) | (inside ? HIT_INSIDE : 0u));
-          st4(&pv.hpos[cur_buf][path], h.pos.x, h.pos.y, h.pos.z, h.t);
-          st4(&pv.hnrm[cur_buf][path], h.normal.x, h.normal.y, h.normal.z, w);
-        }
+      if (finished) {  // (distance, slot | inside | which): position and normal are completed by finalize_hit in k_shade
+        R w;
+        set_code(w, best.ref == kNone ? HIT_MISS : ((best.ref & REF_SLOT_MASK) | (best.which & 2 ? HIT_INSIDE : 0u) | (best.which & 1 ? HIT_SECOND : 0u)));
+        st4(&pv.hpos[cur_buf][path], R(0), R(0), R(0), best.t);
+        st4(&pv.hnrm[cur_buf][path], R(0), R(0), R(0), w);
         finished = false;
       }
       if (exhausted) {
@@ -1169,6 +1163,16 @@ __global__ void __launch_bounds__(kStreamThreads) k_shade(SceneView<R> sc, Param
     V4<R> hp = ld4(&pv.hpos[cur][path]);
     V4<R> hn = ld4(&pv.hnrm[cur][path]);
     const uint32_t code = code_of(hn.w);
+    if (code != HIT_MISS) {  // complete the Hit record: it is also the next ray's origin and skip hit
+      V3<R> ro = xyz(ld4(&pv.hpos[cur ^ 1][path])), rd = xyz(ld4(&pv.dir[path]));
+      V3<R> fp, fn;
+      R ft;
+      finalize_hit<R>(sc, code, ro, rd, fp, fn, ft);
+      hp.x = fp.x; hp.y = fp.y; hp.z = fp.z; hp.w = ft;
+      hn.x = fn.x; hn.y = fn.y; hn.z = fn.z;
+      st4(&pv.hpos[cur][path], hp.x, hp.y, hp.z, hp.w);
+      st4(&pv.hnrm[cur][path], hn.x, hn.y, hn.z, hn.w);
+    }
     bool done = false;
     R out_r = 0, out_g = 0, out_b = 0;
     int dbg = 0;  // BounceType.Skipped
@@ -1406,12 +1410,21 @@ __global__ void __launch_bounds__(kStreamThreads) k_import_rays(SceneView<R> sc,
 }
 
 template <typename R>
-__global__ void __launch_bounds__(kStreamThreads) k_export_hits(SceneView<R> sc, int64_t n, PathView<R> pv, int cur, rtc_hit* out) {
+__global__ void __launch_bounds__(kStreamThreads) k_export_hits(SceneView<R> sc, int64_t n, PathView<R> pv, int cur, rtc_hit* out,
+                                                                 int finalize) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   V4<R> hp = ld4(&pv.hpos[cur][i]);
   V4<R> hn = ld4(&pv.hnrm[cur][i]);
   uint32_t code = code_of(hn.w);
+  if (finalize && code != HIT_MISS) {  // straight after k_trace; after k_shade the record is already complete
+    V3<R> ro = xyz(ld4(&pv.hpos[cur ^ 1][i])), rd = xyz(ld4(&pv.dir[i]));
+    V3<R> fp, fn;
+    R ft;
+    finalize_hit<R>(sc, code, ro, rd, fp, fn, ft);
+    hp.x = fp.x; hp.y = fp.y; hp.z = fp.z; hp.w = ft;
+    hn.x = fn.x; hn.y = fn.y; hn.z = fn.z;
+  }
   rtc_hit h;
   if (code == HIT_MISS) {
     h.prim = -1;
@@ -1523,8 +1536,8 @@ cudaError_t Kernels<R>::import_rays(const LaunchCfg& cfg, const SceneView<R>& sc
 
 template <typename R>
 cudaError_t Kernels<R>::export_hits(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const PathView<R>& pv, int cur,
-                                    rtc_hit* out) {
-  k_export_hits<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, n, pv, cur, out);
+                                    rtc_hit* out, bool finalize) {
+  k_export_hits<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, n, pv, cur, out, finalize ? 1 : 0);
   return cudaGetLastError();
 }
 

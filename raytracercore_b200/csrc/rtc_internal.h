@@ -39,6 +39,7 @@ constexpr uint32_t REF_VNORMALS_AUX = 0x40000000u;  // flag kept in aux[] for ve
 // hit code stored in the w lane of the hit-normal vector
 constexpr uint32_t HIT_MISS = 0xFFFFFFFFu;
 constexpr uint32_t HIT_INSIDE = 1u << 30;
+constexpr uint32_t HIT_SECOND = 1u << 29;  // the hit is the second entry of the primitive's Hit[] (a sphere's far hit)
 
 constexpr uint32_t Q_DEAD = 0x80000000u;  // queue entry flag written by shade for terminated paths
 
@@ -190,7 +191,7 @@ struct Kernels {
   static cudaError_t import_rays(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const rtc_ray* rays,
                                  const rtc_hit* skip, const int32_t* id_to_slot, const PathView<R>& pv, int prev);
   static cudaError_t export_hits(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const PathView<R>& pv, int cur,
-                                 rtc_hit* out);
+                                 rtc_hit* out, bool finalize);
   static cudaError_t export_radiance(const LaunchCfg& cfg, const Band& band, const ParamsView<R>& par,
                                      const PathView<R>& pv, double* out_rgb);
   static int trace_blocks_per_sm();
