@@ -676,7 +676,7 @@ constexpr int kStreamThreads = 256;
 #define RTC_TRACE_THREADS 128
 #endif
 #ifndef RTC_TRACE_MIN_BLOCKS
-#define RTC_TRACE_MIN_BLOCKS 5
+#define RTC_TRACE_MIN_BLOCKS 6
 #endif
 #ifndef RTC_Q8_PRMT
 #define RTC_Q8_PRMT 0
