@@ -98,6 +98,7 @@ namespace RaytracerCore.Raytracing.Gpu
 		[DllImport(Lib)] public static extern int rtc_accum_device_ptrs(IntPtr ctx, out IntPtr rgbSum, out IntPtr samples, out IntPtr misses);
 		[DllImport(Lib)] public static extern int rtc_tonemap_argb(IntPtr ctx, double exposure, double* backRgb, double backA, int* argb);
 		[DllImport(Lib)] public static extern int rtc_debug_trace(IntPtr ctx, int x, int y, uint sample, int capacity, RtcDebugRay* rays, out int n);
+		[DllImport(Lib)] public static extern int rtc_debug_raycast(IntPtr ctx, int mode, int* ids);
 		[DllImport(Lib)] public static extern int rtc_render_samples(IntPtr ctx, uint sample, double* rgb);
 		[DllImport(Lib)] public static extern int rtc_comm_unique_id(byte* id128);
 		[DllImport(Lib)] public static extern int rtc_comm_init(IntPtr ctx, int nRanks, int rank, byte* id128);

@@ -232,6 +232,14 @@ int rtc_tonemap_argb(rtc_ctx* ctx, double exposure, const double back_rgb[3], do
 /* ---- inspection ------------------------------------------------------------------------------------ */
 /* Raytracer.GetDebugTrace(x, y) (Raytracer.cs:254-260,289-292) for one (pixel, sample); *n <= recursion+1. */
 int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t capacity, rtc_debug_ray* out, int32_t* n);
+/* DebugRaycaster.RenderDebug's per-pixel query (DebugRaycaster.cs:170-265): one unjittered camera ray per pixel
+ * (camera.GetRay(x, y).Offset(imagePlane), :236). out is width*height int32, row-major.
+ *   RTC_OVERLAY_PRIMITIVES        Primitive.ID of Scene.RayTrace(ray, null), or -1            (DisplayMode.Primitives, :194-199)
+ *   RTC_OVERLAY_BOUNDING_VOLUMES  BVH.GetIntersectionCount(ray) over the reference-shaped tree (DisplayMode.BoundingVolumes,
+ *                                 :200-212, BVH.cs:352-363); needs a tree from rtc_upload_bvh / rtc_build_bvh
+ * The colour mapping (ColorRotation, alpha from the box count) stays on the host. */
+enum { RTC_OVERLAY_PRIMITIVES = 0, RTC_OVERLAY_BOUNDING_VOLUMES = 1 };
+int rtc_debug_raycast(rtc_ctx* ctx, int32_t mode, int32_t* out);
 /* Per-path radiance of one sample pass (== the DoubleColor[w,h] a tile hands to OnTileFinished,
  * Raytracer.cs:305-326), rgb = (-1,-1,-1) for misses. out is w*h*3 doubles over the full image. */
 int rtc_render_samples(rtc_ctx* ctx, uint32_t sample, double* out_rgb);

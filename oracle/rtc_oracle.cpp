@@ -864,6 +864,32 @@ void orc_debug_trace(orc_scene* s, int32_t x, int32_t y, uint32_t sample, int32_
   *n = cnt;
 }
 
+static int intersection_count(const orc_scene& s, int ni, const Ray& ray) {  // BVH.GetIntersectionCount, BVH.cs:352-363
+  const Node& nd = s.nodes[ni];
+  double n, f;
+  bool hit = aabb_intersect(nd.bmin, nd.bmax, ray, n, f) && f >= 0;
+  if (!hit) return 0;
+  if (nd.prim >= 0) return 1;
+  return 1 + intersection_count(s, nd.left, ray) + intersection_count(s, nd.right, ray);
+}
+
+void orc_debug_raycast(orc_scene* s, int32_t mode, int32_t* out) {
+  const int w = s->par.width, h = s->par.height;
+  std::vector<BI> list;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      Ray ray = ray_offset(camera_get_ray(s->cam, x, y), s->cam.image_plane);  // DebugRaycaster.cs:236
+      int v;
+      if (mode == 0) {
+        Hit hit = scene_ray_trace_bvh(*s, ray, Hit{}, list);  // :194
+        v = hit.prim;
+      } else {
+        v = s->root >= 0 ? intersection_count(*s, s->root, ray) : 0;  // :204
+      }
+      out[(size_t)y * w + x] = v;
+    }
+}
+
 void orc_tonemap(int32_t w, int32_t h, const double* rgb_sum, const uint32_t* samples, const uint32_t* misses,
                  double exposure, const double back[3], double back_a, uint32_t* argb) {
   auto code = [](double r, double g, double b, double a) -> uint32_t {  // SampleSet.GetColorCode, :47-53

@@ -51,6 +51,10 @@ void orc_render_samples(orc_scene* s, uint32_t sample, int threads, double* out_
 void orc_debug_trace(orc_scene* s, int32_t x, int32_t y, uint32_t sample, int32_t capacity, rtc_debug_ray* out,
                      int32_t* n);
 
+/* DebugRaycaster.GetColor's queries per pixel (DebugRaycaster.cs:170-215,236): mode 0 = hit Primitive.ID or -1,
+ * mode 1 = BVH.GetIntersectionCount (BVH.cs:352-363). out: w*h int32. */
+void orc_debug_raycast(orc_scene* s, int32_t mode, int32_t* out);
+
 /* SampleSet.GetOutput over a whole image (SampleSet.cs:61-113, FullRaytracer.cs:179-205). */
 void orc_tonemap(int32_t w, int32_t h, const double* rgb_sum, const uint32_t* samples, const uint32_t* misses,
                  double exposure, const double back_rgb[3], double back_a, uint32_t* argb);

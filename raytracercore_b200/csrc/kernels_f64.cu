@@ -43,6 +43,41 @@ __global__ void k_tonemap(int32_t n, const double* __restrict__ rgb_sum, const u
   argb[i] = color_code(r, g, b, a);
 }
 
+// BVH<T>.GetIntersectionCount (Acceleration/BVH.cs:352-363): 1 + count(left) + count(right) for every node whose
+// Volume.Intersect(ray).far >= 0; leaves count 1. One thread per pixel, explicit stack over the reference-shaped tree.
+__global__ void k_overlay_boxcount(const rtc_bvh_node* __restrict__ nodes, int32_t root, CameraView<double> cam, int32_t width,
+                                   int32_t height, int32_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width * height) return;
+  const int x = i % width, y = i / width;
+  V3<double> o, d;
+  camera_get_ray(cam, (double)x, (double)y, o, d);
+  o = o + (d * cam.image_plane);
+  const V3<double> inv = mk3(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+  int32_t stack[kTraceStack];
+  int sp = 0, count = 0;
+  if (root >= 0) stack[sp++] = root;
+  while (sp > 0) {
+    const rtc_bvh_node& nd = nodes[stack[--sp]];
+    double nr;
+    if (!box_test<double>(nd.bmin[0], nd.bmax[0], nd.bmin[1], nd.bmax[1], nd.bmin[2], nd.bmax[2], o, d, inv, nr)) continue;
+    count++;
+    if (nd.prim < 0 && sp + 2 <= kTraceStack) {
+      stack[sp++] = nd.right;
+      stack[sp++] = nd.left;
+    }
+  }
+  out[i] = count;
+}
+
+cudaError_t launch_overlay_boxcount(cudaStream_t s, const rtc_bvh_node* nodes, int32_t root, const CameraView<double>& cam,
+                                    int32_t width, int32_t height, int32_t* out) {
+  int n = width * height;
+  if (n <= 0) return cudaSuccess;
+  k_overlay_boxcount<<<(n + 127) / 128, 128, 0, s>>>(nodes, root, cam, width, height, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tonemap(cudaStream_t s, int32_t n, const double* rgb_sum, const uint32_t* samples, const uint32_t* misses,
                            double exposure, double br, double bg, double bb, double ba, uint32_t* argb) {
   if (n <= 0) return cudaSuccess;

@@ -1532,6 +1532,61 @@ int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t
   return RTC_OK;
 }
 
+int rtc_debug_raycast(rtc_ctx* ctx, int32_t mode, int32_t* out) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!out) return fail(ctx, RTC_ERR_INVALID, "out must not be null");
+  if (mode != RTC_OVERLAY_PRIMITIVES && mode != RTC_OVERLAY_BOUNDING_VOLUMES) return fail(ctx, RTC_ERR_INVALID, "unknown overlay mode");
+  int rc = ready(ctx, true);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  const int w = ctx->par.width, h = ctx->par.height;
+  const size_t n = (size_t)w * h;
+  int32_t* d_out = nullptr;
+  CU(cudaMalloc((void**)&d_out, n * sizeof(int32_t)));
+  cudaError_t e = cudaSuccess;
+  rtc_bvh_node* d_nodes = nullptr;
+  if (mode == RTC_OVERLAY_BOUNDING_VOLUMES) {
+    if (ctx->nodes.empty()) {
+      cudaFree(d_out);
+      return fail(ctx, RTC_ERR_STATE, "no host-side BVH (the scene came from rtc_upload_baked)");
+    }
+    e = cudaMalloc((void**)&d_nodes, ctx->nodes.size() * sizeof(rtc_bvh_node));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_nodes, ctx->nodes.data(), ctx->nodes.size() * sizeof(rtc_bvh_node), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_overlay_boxcount(ctx->stream, d_nodes, ctx->root, camera_view<double>(ctx->cam), w, h, d_out);
+  } else {
+    auto run = [&](auto tag) -> int {
+      using R = decltype(tag);
+      const int64_t cap = std::max<int64_t>(ctx->max_paths, w);
+      int rc2 = ensure_pool(ctx, cap);
+      if (rc2) return rc2;
+      LaunchCfg cfg{ctx->stream, ctx->sm_count, false};
+      SceneView<R> sv = scene_view<R>(ctx);
+      PathView<R> pv = path_view<R>(ctx);
+      const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(h, cap / w));
+      for (int ya = 0; ya < h; ya += (int)rows) {
+        Band b;
+        b.x0 = 0; b.x1 = w; b.y0 = ya; b.y1 = (int)std::min<int64_t>(h, ya + rows);
+        b.first_sample = 0; b.n_samples = 1;
+        b.n_pix = (uint32_t)(w * (b.y1 - b.y0));
+        b.n_paths = b.n_pix;
+        CU(Kernels<R>::overlay_rays(cfg, camera_view<R>(ctx->cam), params_view<R>(ctx->par), b, pv));
+        CU(Kernels<R>::trace(cfg, sv, pv, 0, 1, 0, true));
+        CU(Kernels<R>::overlay_prims(cfg, sv, params_view<R>(ctx->par), b, pv, 0, d_out));
+      }
+      return RTC_OK;
+    };
+    rc = ctx->precision == RTC_F64 ? run(double()) : run(float());
+  }
+  if (rc == RTC_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  else cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out);
+  if (d_nodes) cudaFree(d_nodes);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("debug_raycast: ") + cudaGetErrorString(e));
+  return RTC_OK;
+}
+
 int rtc_get_stats(rtc_ctx* ctx, rtc_stats* stats) {
   if (!ctx || !stats) return RTC_ERR_INVALID;
   cudaSetDevice(ctx->device);

@@ -1455,6 +1455,41 @@ __global__ void __launch_bounds__(kStreamThreads) k_export_radiance(Band band, P
   out_rgb[g * 3 + 2] = (double)c.z;
 }
 
+// ---- DebugRaycaster overlay (Raytracing/DebugRaycaster.cs:170-265) -----------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(kStreamThreads) k_overlay_rays(CameraView<R> cam, ParamsView<R> par, Band band, PathView<R> pv) {
+  uint32_t path = blockIdx.x * blockDim.x + threadIdx.x;
+  if (path == 0) {
+    pv.ctl->count[0] = band.n_paths;
+    pv.ctl->count[1] = 0;
+    pv.ctl->work_trace = 0;
+  }
+  if (path >= band.n_paths) return;
+  int x, y;
+  uint32_t sample;
+  band_pixel(band, path, x, y, sample);
+  V3<R> o, d;
+  camera_get_ray(cam, R(x), R(y), o, d);  // camera.GetRay(x, y)
+  o = o + (d * cam.image_plane);          // .Offset(camera.imagePlane), DebugRaycaster.cs:236
+  st4(&pv.dir[path], d.x, d.y, d.z, R(0));
+  st4(&pv.hpos[1][path], o.x, o.y, o.z, R(0));
+  R w;
+  set_code(w, HIT_MISS);
+  st4(&pv.hnrm[1][path], R(0), R(0), R(0), w);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kStreamThreads) k_overlay_prims(SceneView<R> sc, ParamsView<R> par, Band band, PathView<R> pv,
+                                                                   int cur, int32_t* out) {
+  uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= band.n_pix) return;
+  uint32_t rw = (uint32_t)(band.x1 - band.x0);
+  uint32_t py = pix / rw;
+  size_t g = (size_t)(band.y0 + (int)py) * par.width + (band.x0 + (int)(pix - py * rw));
+  const uint32_t code = code_of(pv.hnrm[cur][pix].w);
+  out[g] = code == HIT_MISS ? -1 : sc.prim_id[code & REF_SLOT_MASK];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------------------
@@ -1538,6 +1573,20 @@ template <typename R>
 cudaError_t Kernels<R>::export_hits(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const PathView<R>& pv, int cur,
                                     rtc_hit* out, bool finalize) {
   k_export_hits<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, n, pv, cur, out, finalize ? 1 : 0);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Kernels<R>::overlay_rays(const LaunchCfg& cfg, const CameraView<R>& cam, const ParamsView<R>& par, const Band& band,
+                                     const PathView<R>& pv) {
+  k_overlay_rays<R><<<div_up(band.n_paths, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(cam, par, band, pv);
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t Kernels<R>::overlay_prims(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,
+                                      const PathView<R>& pv, int cur, int32_t* out) {
+  k_overlay_prims<R><<<div_up(band.n_pix, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, par, band, pv, cur, out);
   return cudaGetLastError();
 }
 

@@ -194,8 +194,17 @@ struct Kernels {
                                  rtc_hit* out, bool finalize);
   static cudaError_t export_radiance(const LaunchCfg& cfg, const Band& band, const ParamsView<R>& par,
                                      const PathView<R>& pv, double* out_rgb);
+  // DebugRaycaster overlay: unjittered camera rays of a band into the path pool / hit primitive ids out of it
+  static cudaError_t overlay_rays(const LaunchCfg& cfg, const CameraView<R>& cam, const ParamsView<R>& par, const Band& band,
+                                  const PathView<R>& pv);
+  static cudaError_t overlay_prims(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,
+                                   const PathView<R>& pv, int cur, int32_t* out);
   static int trace_blocks_per_sm();
 };
+
+// BVH.GetIntersectionCount per pixel over the reference-shaped (binary, f64) tree; f64 arithmetic in both modes.
+cudaError_t launch_overlay_boxcount(cudaStream_t s, const rtc_bvh_node* nodes, int32_t root, const CameraView<double>& cam,
+                                    int32_t width, int32_t height, int32_t* out);
 
 // mode-independent
 cudaError_t launch_tonemap(cudaStream_t s, int32_t n, const double* rgb_sum, const uint32_t* samples,

@@ -187,6 +187,12 @@ class Context:
         self._ck(N.lib.rtc_debug_trace(self._h, x, y, sample, capacity, buf, C.byref(n)))
         return [buf[i] for i in range(n.value)]
 
+    def debug_raycast(self, mode):
+        """DebugRaycaster overlay query: mode 0 = primitive ids (-1 none), 1 = BVH box-intersection counts."""
+        out = np.zeros((self.height, self.width), dtype=np.int32)
+        self._ck(N.lib.rtc_debug_raycast(self._h, mode, _ptr(out)))
+        return out
+
     def stats(self):
         s = N.Stats()
         self._ck(N.lib.rtc_get_stats(self._h, C.byref(s)))

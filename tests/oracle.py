@@ -30,6 +30,7 @@ def _load():
     lib.orc_render.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_int, P, P, P]
     lib.orc_render_samples.argtypes = [P, C.c_uint32, C.c_int, P]
     lib.orc_debug_trace.argtypes = [P, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(N.DebugRay), C.POINTER(C.c_int32)]
+    lib.orc_debug_raycast.argtypes = [P, C.c_int32, P]
     lib.orc_tonemap.argtypes = [C.c_int32, C.c_int32, P, P, P, C.c_double, C.POINTER(C.c_double), C.c_double, P]
     lib.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.orc_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
@@ -108,6 +109,11 @@ class OracleScene:
     def render_samples(self, sample, threads=NTHREADS):
         out = np.zeros((self.height, self.width, 3))
         lib.orc_render_samples(self._h, sample, threads, _ptr(out))
+        return out
+
+    def debug_raycast(self, mode):
+        out = np.zeros((self.height, self.width), dtype=np.int32)
+        lib.orc_debug_raycast(self._h, mode, _ptr(out))
         return out
 
     def debug_trace(self, x, y, sample, capacity=64):

@@ -304,3 +304,22 @@ def test_baked_scene_image_round_trip():
         for c in (ctx, ctx2, other):
             c.close()
         baked.close()
+
+
+def test_debug_raycaster_overlays():
+    """DebugRaycaster's per-pixel queries (primitive ids, BVH box counts) against the oracle."""
+    for make in (cornell, die):
+        sc = make(72, 48)
+        ora = O.OracleScene(sc, seed=1)
+        want_p, want_b = ora.debug_raycast(0), ora.debug_raycast(1)
+        assert (want_p >= 0).mean() > 0.2 and want_b.max() > 5
+        for prec in (RTC_F64, RTC_F32):
+            ctx = Context(0, prec)
+            ctx.load(sc, seed=1)
+            got_p, got_b = ctx.debug_raycast(0), ctx.debug_raycast(1)
+            assert np.array_equal(got_b, want_b)  # box counts are evaluated in f64 in both modes
+            if prec == RTC_F64:
+                assert np.array_equal(got_p, want_p)
+            else:
+                assert (got_p != want_p).mean() < 0.01  # unjittered rays land exactly on shared edges: f32 ties
+            ctx.close()
