@@ -72,7 +72,7 @@ struct TimedLaunch {
 // Host-resident image of the device scene layout (one pinned buffer + segment table): what Scene.Prepare leaves
 // behind on the host side, uploadable with plain H2D copies.
 struct rtc_baked {
-  enum { S_NODES, S_QNODES, S_UNBOUNDED, S_PRIMS, S_MATS, S_XFORMS, S_AUX, S_PRIM_ID, S_ID_TO_SLOT, S_PRIM_REF, S_COUNT };
+  enum { S_NODES, S_QNODES, S_UNBOUNDED, S_PRIMS, S_MATS, S_XFORMS, S_AUX, S_PRIM_ID, S_ID_TO_SLOT, S_PRIM_NZ, S_COUNT };
   int precision = RTC_F32;
   int32_t n_prims = 0, n_unbounded = 0, n_xforms = 0, bvh_depth = 0;
   uint32_t root_node = 0;
@@ -121,7 +121,7 @@ struct rtc_ctx {
   // device scene
   void *d_nodes = nullptr, *d_prims = nullptr, *d_xforms = nullptr, *d_mats = nullptr;
   int32_t *d_aux = nullptr, *d_prim_id = nullptr, *d_id_to_slot = nullptr;
-  uint32_t* d_prim_ref = nullptr;
+  void* d_prim_nz = nullptr;
   void* d_qnodes = nullptr;       // f32 mode: CNode[]
   uint32_t* d_unbounded = nullptr;  // f32 mode: leaf refs of primitives with infinite boxes
   int32_t n_unbounded = 0;
@@ -192,7 +192,7 @@ void free_scene_device(rtc_ctx* c) {
   free_dev_t(c->d_aux);
   free_dev_t(c->d_prim_id);
   free_dev_t(c->d_id_to_slot);
-  free_dev_t(c->d_prim_ref);
+  free_dev_t(c->d_prim_nz);
   free_dev(c->d_qnodes);
   free_dev_t(c->d_unbounded);
   c->n_unbounded = 0;
@@ -261,12 +261,13 @@ SceneView<R> scene_view(rtc_ctx* c) {
   sv.mats = (const DMat<R>*)c->d_mats;
   sv.aux = c->d_aux;
   sv.prim_id = c->d_prim_id;
-  sv.prim_ref = c->d_prim_ref;
+  sv.prim_nz = (const R*)c->d_prim_nz;
   sv.root = c->root_node;
   sv.n_prims = c->n_prims;
   sv.qnodes = (const CNode*)c->d_qnodes;
   sv.unbounded = c->d_unbounded;
   sv.n_unbounded = c->n_unbounded;
+  sv.q_stack = std::max(2, c->bvh_depth + 1);
   return sv;
 }
 
@@ -306,6 +307,13 @@ ParamsView<R> params_view(const rtc_params& p) {
   return v;
 }
 
+// raw bits into the w lane of a record (matches code_of / set_code on the device)
+inline void set_ref_bits(float& w, uint32_t bits) { std::memcpy(&w, &bits, 4); }
+inline void set_ref_bits(double& w, uint32_t bits) {
+  const uint64_t b = bits;
+  std::memcpy(&w, &b, 8);
+}
+
 // f64 -> R with outward rounding for box bounds
 template <typename R>
 R round_down(double x) {
@@ -332,7 +340,7 @@ R round_up(double x) {
 int upload_baked_image(rtc_ctx* ctx, const rtc_baked* bk) {
   void** dst[rtc_baked::S_COUNT] = {&ctx->d_nodes, &ctx->d_qnodes, (void**)&ctx->d_unbounded, &ctx->d_prims, &ctx->d_mats,
                                     &ctx->d_xforms, (void**)&ctx->d_aux, (void**)&ctx->d_prim_id, (void**)&ctx->d_id_to_slot,
-                                    (void**)&ctx->d_prim_ref};
+                                    &ctx->d_prim_nz};
   for (int i = 0; i < rtc_baked::S_COUNT; i++) {
     const size_t need = std::max<size_t>(bk->bytes[i], 16);
     if (ctx->seg_cap[i] < need || !*dst[i]) {
@@ -761,8 +769,8 @@ int build_device_scene(rtc_ctx* ctx) {
       std::fprintf(stderr, "[rtcore_b200] q8 tree: %zu nodes, %.2f children/node (%.2f leaves/node), depth %d, %d bounded prims\n",
                    qn.size(), qn.empty() ? 0.0 : (double)kids_total / qn.size(), qn.empty() ? 0.0 : (double)leaf_total / qn.size(), max_depth, n_bounded);
     }
-    if (max_depth + 1 > kQStack)
-      return fail(ctx, RTC_ERR_UNSUPPORTED, "8-wide BVH depth " + std::to_string(max_depth) + " exceeds the traversal stack (" + std::to_string(kQStack - 1) + ")");
+    if (max_depth + 1 > kQStackMax)
+      return fail(ctx, RTC_ERR_UNSUPPORTED, "8-wide BVH depth " + std::to_string(max_depth) + " exceeds the traversal stack (" + std::to_string(kQStackMax - 1) + ")");
     ctx->bvh_depth = max_depth;
     // unbounded primitives keep their left-first order, after the bounded ones
     for (int32_t li = 0; li < n; li++) {
@@ -780,6 +788,7 @@ int build_device_scene(rtc_ctx* ctx) {
   std::vector<DMat<R>> dm(n);
   std::vector<int32_t> aux(n, -1), prim_id(n), id_to_slot(n);
   std::vector<uint32_t> prim_ref(n);
+  std::vector<R> prim_nz(n, R(0));
   for (int32_t i = 0; i < nn; i++) {
     if (leaf_slot[i] < 0) continue;
     prim_ref[leaf_slot[i]] = leaf_ref(i);
@@ -796,12 +805,14 @@ int build_device_scene(rtc_ctx* ctx) {
     if (k == RTC_KIND_TRIANGLE) {
       d.a.x = (R)g[0]; d.a.y = (R)g[1]; d.a.z = (R)g[2]; d.a.w = (R)g[9];
       d.b.x = (R)g[3]; d.b.y = (R)g[4]; d.b.z = (R)g[5]; d.b.w = (R)g[10];
-      d.c.x = (R)g[6]; d.c.y = (R)g[7]; d.c.z = (R)g[8]; d.c.w = (R)g[11];
+      d.c.x = (R)g[6]; d.c.y = (R)g[7]; d.c.z = (R)g[8];
+      prim_nz[s] = (R)g[11];
       if ((f & RTC_FLAG_VNORMALS) && ctx->xform[p] >= 0) aux[s] = ctx->xform[p] | (int32_t)REF_VNORMALS_AUX;
     } else {
       d.a.x = (R)g[0]; d.a.y = (R)g[1]; d.a.z = (R)g[2]; d.a.w = (R)g[3];
       if (k == RTC_KIND_SPHERE && (f & RTC_FLAG_TRANSFORMED) && ctx->xform[p] >= 0) aux[s] = ctx->xform[p];
     }
+    set_ref_bits(d.c.w, prim_ref[s]);  // the leaf reference rides in the record (one round trip per leaf test)
     const double* m = &ctx->material[(size_t)p * RTC_MATERIAL_STRIDE];
     DMat<R>& dmat = dm[s];
     bool reflective = m[13] > 0;  // Primitive.IsReflective (Primitive.cs:106): Specular/Refraction read black otherwise
@@ -837,11 +848,11 @@ int build_device_scene(rtc_ctx* ctx) {
   bk->bvh_depth = ctx->bvh_depth;
   bk->root_node = ctx->root_node;
   const void* src[rtc_baked::S_COUNT] = {dn.data(), qn.data(), unbounded.data(), dp.data(), dm.data(), dx.data(),
-                                         aux.data(), prim_id.data(), id_to_slot.data(), prim_ref.data()};
+                                         aux.data(), prim_id.data(), id_to_slot.data(), prim_nz.data()};
   const size_t sz[rtc_baked::S_COUNT] = {dn.size() * sizeof(DNode<R>), qn.size() * sizeof(CNode), unbounded.size() * sizeof(uint32_t),
                                          dp.size() * sizeof(DPrim<R>), dm.size() * sizeof(DMat<R>), dx.size() * sizeof(DXform<R>),
                                          aux.size() * sizeof(int32_t), prim_id.size() * sizeof(int32_t),
-                                         id_to_slot.size() * sizeof(int32_t), prim_ref.size() * sizeof(uint32_t)};
+                                         id_to_slot.size() * sizeof(int32_t), prim_nz.size() * sizeof(R)};
   size_t total = 0;
   for (int i = 0; i < rtc_baked::S_COUNT; i++) {
     bk->off[i] = total;

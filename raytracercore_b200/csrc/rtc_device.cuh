@@ -275,17 +275,23 @@ __device__ __forceinline__ V3<R> create_horizon(const V3<R>& pole, R z, R theta)
 template <typename R>
 struct Cand {
   R t;
-  V3<R> pos;
+  V3<R> pos;     // only filled when with_pos<R, WITH_NORMAL>()
   V3<R> normal;  // only filled when WITH_NORMAL
   bool inside;
 };
+// The f32 traversal does not carry hit positions: its self-hit rule tolerates origin + t * direction, which
+// consider_cand forms on the rare occasion a candidate lies on the skip primitive. f64 keeps the reference's exact forms.
+template <typename R, bool WITH_NORMAL>
+__device__ __forceinline__ constexpr bool with_pos() { return WITH_NORMAL || Num<R>::is_f64; }
 
 // Triangle.RayTraceAVXFaster + GetNormal (Primitives/Triangle.cs:77-146, 209-224)
-template <typename R, bool WITH_NORMAL>
-__device__ __forceinline__ int tri_hits(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
+// FORCE (finalize_hit): the traversal has already accepted this candidate; recompute its record without re-deciding the
+// hit (the f32 units are compiled with FMA contraction, so the same test inlined in two kernels may round differently
+// on an edge) and with the inside flag the traversal reported.
+template <typename R, bool WITH_NORMAL, bool FORCE = false>
+__device__ __forceinline__ int tri_hits(const SceneView<R>& sc, uint32_t ref, const V4<R>& A, const V4<R>& B, const V4<R>& C,
+                                        const V3<R>& o, const V3<R>& d, Cand<R>* out, bool forced_inside = false) {
   const uint32_t slot = ref & REF_SLOT_MASK;
-  const DPrim<R>* pr = sc.prims + slot;
-  V4<R> A = ldg4(&pr->a), B = ldg4(&pr->b), C = ldg4(&pr->c);
   V3<R> v0 = xyz(A), e1 = xyz(B), e2 = xyz(C);
   V3<R> off = o - v0;                // :84
   V3<R> s1 = scross3(off, e1);       // :85
@@ -305,13 +311,14 @@ __device__ __forceinline__ int tri_hits(const SceneView<R>& sc, uint32_t ref, co
   else
     reject |= (u + v) > 1;
   reject |= dist < 0;                // :120
-  if (reject) return 0;
-  bool inside = inv < 0;             // :126
+  if (!FORCE && reject) return 0;
+  bool inside = FORCE ? forced_inside : (inv < 0);  // :126
   out[0].t = dist;
   out[0].inside = inside;
-  out[0].pos = mk3(rfma(e1.x, u, rfma(e2.x, v, v0.x)), rfma(e1.y, u, rfma(e2.y, v, v0.y)), rfma(e1.z, u, rfma(e2.z, v, v0.z)));  // :130
+  if (with_pos<R, WITH_NORMAL>())
+    out[0].pos = mk3(rfma(e1.x, u, rfma(e2.x, v, v0.x)), rfma(e1.y, u, rfma(e2.y, v, v0.y)), rfma(e1.z, u, rfma(e2.z, v, v0.z)));  // :130
   if (WITH_NORMAL) {
-    V3<R> N = mk3(A.w, B.w, C.w);
+    V3<R> N = mk3(A.w, B.w, __ldg(&sc.prim_nz[slot]));
     int32_t ax = sc.aux[slot];
     if (ax >= 0 && (ax & REF_VNORMALS_AUX)) {  // :211-219 (weights and the zero face normal are the reference's)
       const DXform<R>* xf = sc.xforms + (ax & 0x3FFFFFFF);
@@ -327,18 +334,15 @@ __device__ __forceinline__ int tri_hits(const SceneView<R>& sc, uint32_t ref, co
   return 1;
 }
 
-// Sphere.RayTraceAVX (Primitives/Sphere.cs:50-155)
-template <typename R, bool WITH_NORMAL>
-__device__ __forceinline__ int sphere_hits(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
-  const uint32_t slot = ref & REF_SLOT_MASK;
-  V4<R> A = ldg4(&sc.prims[slot].a);
+// Sphere.RayTraceAVX (Primitives/Sphere.cs:50-155). `x` = the sphere's matrix rows when it is transformed, else nullptr.
+template <typename R, bool WITH_NORMAL, bool FORCE = false>
+__device__ __forceinline__ int sphere_hits(const DXform<R>* x, const V4<R>& A, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
   V3<R> C = xyz(A);
   R radius = A.w;
-  const bool xf = ((ref >> REF_KIND_SHIFT) & 3) == DK_XSPHERE;
+  const bool xf = x != nullptr;
   V3<R> oo = o, od = d;
   V4<R> rows[9];
   if (xf) {  // :58-76
-    const DXform<R>* x = sc.xforms + sc.aux[slot];
 #pragma unroll
     for (int i = 0; i < 9; i++) rows[i] = ldg4(&x->r[i]);
     oo = xf_point(rows, o);
@@ -357,6 +361,7 @@ __device__ __forceinline__ int sphere_hits(const SceneView<R>& sc, uint32_t ref,
     R bp = -dot3(off, od);
     V3<R> l = mk3(rfma(bp, od.x, off.x), rfma(bp, od.y, off.y), rfma(bp, od.z, off.z));
     R disc = radius * radius - dot3(l, l);
+    if (FORCE) disc = fmaxf(disc, R(0));  // an accepted grazing hit keeps a real root
     R c = dot3(off, off) - radius * radius;
     R sq = rsqrt_(disc);  // NaN when the ray misses
     const bool fwd = bp >= 0;  // (-0 counts as forward: q must not cancel)
@@ -371,7 +376,7 @@ __device__ __forceinline__ int sphere_hits(const SceneView<R>& sc, uint32_t ref,
     }
     if (risnan(sq)) t_far = Num<R>::nan();
   }
-  if (!(t_far >= 0) && !xf) return 0;  // (for transformed spheres the test applies to the re-measured distances)
+  if (!FORCE && !(t_far >= 0) && !xf) return 0;  // (for transformed spheres the test applies to the re-measured distances)
   V3<R> pf = mk3(rfma(t_far, od.x, oo.x), rfma(t_far, od.y, oo.y), rfma(t_far, od.z, oo.z));      // :94
   V3<R> pc = mk3(rfma(t_close, od.x, oo.x), rfma(t_close, od.y, oo.y), rfma(t_close, od.z, oo.z));  // :97
   V3<R> nf, nc;
@@ -388,22 +393,24 @@ __device__ __forceinline__ int sphere_hits(const SceneView<R>& sc, uint32_t ref,
     }
     t_far = dot3(d, pf - o);
     t_close = dot3(d, pc - o);
-    if (!(t_far >= 0)) return 0;  // :145-146
+    if (!FORCE && !(t_far >= 0)) return 0;  // :145-146
   }
   if (WITH_NORMAL) nf = neg3(nf);  // :142
-  if (!(t_close >= 0)) {           // :148-149
+  if (!FORCE && !(t_close >= 0)) {  // :148-149 (FORCE: always [near, far]; finalize_hit picks by the reported inside flag)
     out[0].t = t_far;
-    out[0].pos = pf;
+    if (with_pos<R, WITH_NORMAL>()) out[0].pos = pf;
     out[0].inside = true;
     if (WITH_NORMAL) out[0].normal = nf;
     return 1;
   }
   out[0].t = t_close;  // :151-154
-  out[0].pos = pc;
   out[0].inside = false;
   out[1].t = t_far;
-  out[1].pos = pf;
   out[1].inside = true;
+  if (with_pos<R, WITH_NORMAL>()) {
+    out[0].pos = pc;
+    out[1].pos = pf;
+  }
   if (WITH_NORMAL) {
     out[0].normal = nc;
     out[1].normal = nf;
@@ -424,29 +431,27 @@ __device__ __forceinline__ bool nearly_equal(R a, R b, R delta) {
 }
 
 // Plane.DoRayTrace (Primitives/Plane.cs:36-66)
-template <typename R, bool WITH_NORMAL>
-__device__ __forceinline__ int plane_hits(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
-  const uint32_t slot = ref & REF_SLOT_MASK;
-  V4<R> A = ldg4(&sc.prims[slot].a);
+template <typename R, bool WITH_NORMAL, bool FORCE = false>
+__device__ __forceinline__ int plane_hits(const V4<R>& A, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
   V3<R> N = xyz(A);
   R od = A.w;
   R ray_dist = dot3(o, N);   // :38
   R denom = dot3(d, N);      // :39
   if (nearly_equal(denom, R(0), denom - R(0)) && nearly_equal(od, ray_dist, od - ray_dist)) {  // :41-42
     out[0].t = 0;
-    out[0].pos = o;
+    if (with_pos<R, WITH_NORMAL>()) out[0].pos = o;
     out[0].inside = true;
     if (WITH_NORMAL) out[0].normal = N;
     return 1;
   }
-  if (denom == 0) return 0;  // :44-45
+  if (!FORCE && denom == 0) return 0;  // :44-45
   R dist = (od - ray_dist) / denom;  // :47
-  if (dist >= (Num<R>::is_f64 ? R(-1e-24) : R(0))) {  // :49
+  if (FORCE || dist >= (Num<R>::is_f64 ? R(-1e-24) : R(0))) {  // :49
     V3<R> hp = o + (d * dist);  // :51
     bool inside = dot3(N, d) > 0;  // :56
     V3<R> dl = hp - o;
     out[0].t = rsqrt_((dl.x * dl.x + dl.y * dl.y) + dl.z * dl.z);  // :62 (hitPos - ray.Origin).Length
-    out[0].pos = hp;
+    if (with_pos<R, WITH_NORMAL>()) out[0].pos = hp;
     out[0].inside = inside;
     if (WITH_NORMAL) out[0].normal = inside ? neg3(N) : N;
     return 1;
@@ -454,45 +459,67 @@ __device__ __forceinline__ int plane_hits(const SceneView<R>& sc, uint32_t ref, 
   return 0;
 }
 
-template <typename R, bool WITH_NORMAL>
-__device__ __forceinline__ int prim_hits(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
+// The primitive record is fetched whole (3 x 16-byte loads issued together); its third vector carries the leaf reference
+// (kind, flags, slot) in the w lane, so a leaf test costs one memory round trip.
+template <typename R>
+struct PrimRec {
+  V4<R> a, b, c;
+};
+template <typename R>
+__device__ __forceinline__ PrimRec<R> load_prim(const SceneView<R>& sc, uint32_t slot) {
+  const DPrim<R>* pr = sc.prims + slot;
+  PrimRec<R> p;
+  p.a = ldg4(&pr->a);
+  p.b = ldg4(&pr->b);
+  p.c = ldg4(&pr->c);
+  return p;
+}
+template <typename R>
+__device__ __forceinline__ uint32_t ref_of(const PrimRec<R>& p) { return code_of(p.c.w); }
+
+template <typename R, bool WITH_NORMAL, bool FORCE = false>
+__device__ __forceinline__ int prim_hits(const SceneView<R>& sc, uint32_t ref, const PrimRec<R>& p, const V3<R>& o, const V3<R>& d,
+                                         Cand<R>* out, bool forced_inside = false) {
   const int kind = (ref >> REF_KIND_SHIFT) & 3;
-  if (kind == DK_TRI) return tri_hits<R, WITH_NORMAL>(sc, ref, o, d, out);
-  if (kind == DK_PLANE) return plane_hits<R, WITH_NORMAL>(sc, ref, o, d, out);
-  return sphere_hits<R, WITH_NORMAL>(sc, ref, o, d, out);
+  if (kind == DK_TRI) return tri_hits<R, WITH_NORMAL, FORCE>(sc, ref, p.a, p.b, p.c, o, d, out, forced_inside);
+  if (kind == DK_PLANE) return plane_hits<R, WITH_NORMAL, FORCE>(p.a, o, d, out);
+  if (kind == DK_XSPHERE)
+    return sphere_hits<R, WITH_NORMAL, FORCE>(sc.xforms + sc.aux[ref & REF_SLOT_MASK], p.a, o, d, out);
+  return sphere_hits<R, WITH_NORMAL, FORCE>(nullptr, p.a, o, d, out);
 }
 
 // The skip hit (previous bounce's Hit) as the trace kernel sees it: primitive slot and inside flag live in
 // registers, the rest (position, distance, normal) stays in the path's previous-hit record and is only read on
-// the rare occasion a candidate lies on the same primitive.
+// the rare occasion a candidate lies on the same primitive. Everything is passed BY VALUE to the out-of-line
+// skip_matches: a by-reference argument would pin the caller's copy (and the candidate arrays) in local memory.
 template <typename R>
 struct Skip {
-  uint32_t slot;  // REF_SLOT_MASK + 1 when there is none
-  bool inside;
-  const V4<R>* hpos;  // xyz = skip position (= ray origin in the render loop), w = skip Hit.Distance
-  const V4<R>* hnrm;  // xyz = skip normal
-  const V4<R>* spos;  // explicit skip position (rtc_trace_closest) or nullptr
+  uint32_t code;  // the previous hit's code (slot | HIT_INSIDE | HIT_SECOND), HIT_MISS when there is none
+  __device__ __forceinline__ uint32_t slot() const { return code == HIT_MISS ? REF_SLOT_MASK + 1 : (code & REF_SLOT_MASK); }
+  __device__ __forceinline__ bool inside() const { return (code & HIT_INSIDE) != 0; }
+};
+template <typename R>
+struct SkipSrc {          // warp-uniform: where the skip records of the wavefront live
+  const V4<R>* hpos;      // [path] xyz = skip position (= ray origin in the render loop), w = skip Hit.Distance
+  const V4<R>* hnrm;      // [path] xyz = skip normal
+  const V4<R>* spos;      // [path] explicit skip position (rtc_trace_closest) or nullptr
 };
 
 // Util.RayHitMatches (Util.cs:179-192) for a candidate on the same primitive as the skip hit.
 template <typename R>
-__device__ __noinline__ bool skip_matches(const SceneView<R>& sc, uint32_t ref, const V3<R>& o, const V3<R>& d, int which,
-                                          bool cand_inside, R cand_t, const V3<R>& cand_pos, const Skip<R>& sk) {
-  if constexpr (!Num<R>::is_f64) {
-    // f32 mode: a flat primitive can only re-hit itself at the ray origin, so the same primitive is always the
-    // self-hit; the positional rule is kept for spheres (their far hit is a legitimate second hit).
-    const int kind = (ref >> REF_KIND_SHIFT) & 3;
-    if (kind == DK_TRI || kind == DK_PLANE) return true;
-  }
-  V4<R> hp = ld4(sk.hpos), hn = ld4(sk.hnrm);
-  V3<R> spos = sk.spos ? xyz(ld4(sk.spos)) : xyz(hp);
+__device__ __noinline__ bool skip_matches(const SceneView<R>* scp, uint32_t ref, V3<R> o, V3<R> d, int which, bool cand_inside,
+                                          R cand_t, V3<R> cand_pos, bool skip_inside, const V4<R>* hpos, const V4<R>* hnrm,
+                                          const V4<R>* sposp) {
+  V4<R> hp = ld4(hpos), hn = ld4(hnrm);
+  V3<R> spos = sposp ? xyz(ld4(sposp)) : xyz(hp);
   V3<R> snrm = xyz(hn);
   if constexpr (Num<R>::is_f64) {
     // `a == b` (Hit.cs:44-59): identical primitive, position, distance, normal and inside flag
-    if (cand_pos.x == spos.x && cand_pos.y == spos.y && cand_pos.z == spos.z && cand_t == hp.w && cand_inside == sk.inside) {
+    if (cand_pos.x == spos.x && cand_pos.y == spos.y && cand_pos.z == spos.z && cand_t == hp.w && cand_inside == skip_inside) {
       Cand<R> full[2];
-      prim_hits<R, true>(sc, ref, o, d, full);
-      const V3<R>& n = full[which].normal;
+      const PrimRec<R> pr = load_prim(*scp, ref & REF_SLOT_MASK);
+      prim_hits<R, true>(*scp, ref, pr, o, d, full);
+      const V3<R> n = which ? full[1].normal : full[0].normal;
       if (n.x == snrm.x && n.y == snrm.y && n.z == snrm.z) return true;
     }
   }
@@ -502,8 +529,8 @@ __device__ __noinline__ bool skip_matches(const SceneView<R>& sc, uint32_t ref, 
   V3<R> dl = cand_pos - spos;
   R ld = (dl.x * dl.x + dl.y * dl.y) + dl.z * dl.z;
   if (!nearly_equal(la, lb, ld)) return false;
-  if (dot3(d, snrm) > 0) return cand_inside != sk.inside;
-  return cand_inside == sk.inside;
+  if (dot3(d, snrm) > 0) return cand_inside != skip_inside;
+  return cand_inside == skip_inside;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -559,39 +586,58 @@ __device__ __forceinline__ bool box_test(R lox, R hix, R loy, R hiy, R loz, R hi
 template <typename R>
 struct Best {
   R t, near_;
-  uint32_t ref;  // 0xFFFFFFFF = none
-  int which;
+  uint32_t code;  // the hit code the path pool stores: slot | HIT_INSIDE | HIT_SECOND, HIT_MISS = none
 };
 
+// One candidate of Primitive.RayTrace (Primitives/Primitive.cs:46-75). Returns true when the candidate is acceptable
+// (the reference's `return curHit`), whether or not it then beats the best hit so far.
 template <typename R>
-__device__ __forceinline__ void test_leaf(const SceneView<R>& sc, uint32_t ref, R leaf_near, const V3<R>& o, const V3<R>& d,
-                                          const Skip<R>& sk, Best<R>& best) {
-  Cand<R> c[2];
-  int n = prim_hits<R, false>(sc, ref, o, d, c);
+__device__ __forceinline__ bool consider_cand(const SceneView<R>& sc, uint32_t ref, int which, bool cand_inside, R t,
+                                              const V3<R>& pos, R leaf_near, const V3<R>& o, const V3<R>& d, const Skip<R>& sk,
+                                              const SkipSrc<R>& src, uint32_t path, Best<R>& best) {
   const uint32_t slot = ref & REF_SLOT_MASK;
-  for (int i = 0; i < n; i++) {  // Primitive.RayTrace, Primitives/Primitive.cs:46-75
-    bool inside = c[i].inside ^ ((ref & REF_INVERT) != 0);  // :60-61, Hit.cs:39-42
-    if (inside && !(ref & REF_TWOSIDED)) continue;          // :63-64
-    if (slot == sk.slot && skip_matches<R>(sc, ref, o, d, i, inside, c[i].t, c[i].pos, sk)) continue;  // :66
-    R t = c[i].t;
-    // Scene.cs:85-86 strict `<`; equal distances fall back to the reference's scan order (Near, then leaf order).
-    // A candidate whose distance is NaN or +inf (the reference's det == 0 artefacts) is never taken.
-    bool take = t < best.t;
-    if (!take && t == best.t && best.ref != 0xFFFFFFFFu) {
-      uint32_t bslot = best.ref & REF_SLOT_MASK;
-      if constexpr (Num<R>::is_f64)
-        take = (leaf_near < best.near_) || (leaf_near == best.near_ && slot < bslot);
-      else
-        take = slot < bslot;  // f32 mode: exact-distance ties go to the lower slot (the box near is not tracked)
+  const bool inside = cand_inside ^ ((ref & REF_INVERT) != 0);  // :60-61, Hit.cs:39-42
+  if (inside && !(ref & REF_TWOSIDED)) return false;            // :63-64
+  if (slot == sk.slot()) {                                      // :66
+    bool same;
+    const int kind = (ref >> REF_KIND_SHIFT) & 3;
+    if (!Num<R>::is_f64 && (kind == DK_TRI || kind == DK_PLANE)) {
+      // f32 mode: a flat primitive can only re-hit itself at the ray origin, so the same primitive is always the
+      // self-hit; the positional rule is kept for spheres (their far hit is a legitimate second hit).
+      same = true;
+    } else {
+      const V3<R> cpos = Num<R>::is_f64 ? pos : o + (d * t);
+      same = skip_matches<R>(Num<R>::is_f64 ? &sc : nullptr, ref, o, d, which, inside, t, cpos, sk.inside(), src.hpos + path, src.hnrm + path,
+                             src.spos ? src.spos + path : nullptr);
     }
-    if (take) {
-      best.t = t;
-      best.near_ = leaf_near;
-      best.ref = ref;
-      best.which = i | (inside ? 2 : 0);
-    }
-    break;  // :68-70 first acceptable hit of this primitive
+    if (same) return false;
   }
+  // Scene.cs:85-86 strict `<`; equal distances fall back to the reference's scan order (Near, then leaf order).
+  // A candidate whose distance is NaN or +inf (the reference's det == 0 artefacts) is never taken.
+  bool take = t < best.t;
+  if (!take && t == best.t && best.code != HIT_MISS) {
+    uint32_t bslot = best.code & REF_SLOT_MASK;
+    if constexpr (Num<R>::is_f64)
+      take = (leaf_near < best.near_) || (leaf_near == best.near_ && slot < bslot);
+    else
+      take = slot < bslot;  // f32 mode: exact-distance ties go to the lower slot (the box near is not tracked)
+  }
+  if (take) {
+    best.t = t;
+    best.near_ = leaf_near;
+    best.code = slot | (inside ? HIT_INSIDE : 0u) | (which ? HIT_SECOND : 0u);
+  }
+  return true;
+}
+
+template <typename R>
+__device__ __forceinline__ void test_leaf(const SceneView<R>& sc, uint32_t ref, const PrimRec<R>& pr, R leaf_near, const V3<R>& o,
+                                          const V3<R>& d, const Skip<R>& sk, const SkipSrc<R>& src, uint32_t path, Best<R>& best) {
+  Cand<R> c[2];  // indexed with constants only: stays in registers
+  const int n = prim_hits<R, false>(sc, ref, pr, o, d, c);
+  bool accepted = false;
+  if (n > 0) accepted = consider_cand<R>(sc, ref, 0, c[0].inside, c[0].t, c[0].pos, leaf_near, o, d, sk, src, path, best);
+  if (n > 1 && !accepted) consider_cand<R>(sc, ref, 1, c[1].inside, c[1].t, c[1].pos, leaf_near, o, d, sk, src, path, best);  // :68-70
 }
 
 // Completes a trace result (distance, slot, inside, which) into the full Hit record (Hit.cs:14-20) by re-evaluating the
@@ -599,15 +645,20 @@ __device__ __forceinline__ void test_leaf(const SceneView<R>& sc, uint32_t ref, 
 template <typename R>
 __device__ __forceinline__ void finalize_hit(const SceneView<R>& sc, uint32_t code, const V3<R>& o, const V3<R>& d, V3<R>& pos,
                                              V3<R>& normal, R& t) {
-  const uint32_t ref = __ldg(&sc.prim_ref[code & REF_SLOT_MASK]);
+  const PrimRec<R> pr = load_prim(sc, code & REF_SLOT_MASK);
+  const uint32_t ref = ref_of(pr);
+  // the primitive's own inside flag (before Primitive.Invert, Primitive.cs:60-61), as the traversal saw it
+  const bool raw_inside = ((code & HIT_INSIDE) != 0) != ((ref & REF_INVERT) != 0);
+  const int kind = (ref >> REF_KIND_SHIFT) & 3;
   Cand<R> c[2];
   c[0].t = c[1].t = Num<R>::nan();
   c[0].pos = c[1].pos = c[0].normal = c[1].normal = mk3(Num<R>::nan(), Num<R>::nan(), Num<R>::nan());
-  prim_hits<R, true>(sc, ref, o, d, c);
-  const Cand<R>& h = c[(code & HIT_SECOND) ? 1 : 0];
-  pos = h.pos;
-  normal = h.normal;
-  t = h.t;
+  prim_hits<R, true, true>(sc, ref, pr, o, d, c, raw_inside);
+  // forced sphere records are [near (outside), far (inside)]; the other kinds have one record
+  const bool second = (kind == DK_SPHERE || kind == DK_XSPHERE) ? raw_inside : false;
+  pos = second ? c[1].pos : c[0].pos;
+  normal = second ? c[1].normal : c[0].normal;
+  t = second ? c[1].t : c[0].t;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -676,13 +727,16 @@ constexpr int kStreamThreads = 256;
 #define RTC_TRACE_THREADS 128
 #endif
 #ifndef RTC_TRACE_MIN_BLOCKS
-#define RTC_TRACE_MIN_BLOCKS 6
+#define RTC_TRACE_MIN_BLOCKS 5
 #endif
 #ifndef RTC_Q8_PRMT
 #define RTC_Q8_PRMT 0
 #endif
 #ifndef RTC_PREFETCH
 #define RTC_PREFETCH 0
+#endif
+#ifndef RTC_Q8_SMEM_STATE
+#define RTC_Q8_SMEM_STATE 1
 #endif
 constexpr int kTraceThreads = RTC_TRACE_THREADS;
 constexpr int kTraceMinBlocks = RTC_TRACE_MIN_BLOCKS;
@@ -723,6 +777,21 @@ __global__ void __launch_bounds__(kStreamThreads) k_camera_rays(CameraView<R> ca
   out[i].dir[0] = d.x; out[i].dir[1] = d.y; out[i].dir[2] = d.z;
 }
 
+// What one trace launch reads and writes, resolved on the host so that every pointer is a kernel parameter (constant
+// bank operand) instead of a value selected on the device that would occupy registers for the whole traversal.
+template <typename R>
+struct TraceIO {
+  const V4<R>* dir;       // [path] ray direction
+  const V4<R>* in_hpos;   // [path] xyz = ray origin = previous hit position, w = previous Hit.Distance
+  const V4<R>* in_hnrm;   // [path] xyz = previous hit normal, w = previous hit code (the skip hit)
+  const V4<R>* skip_pos;  // [path] explicit skip position (rtc_trace_closest) or nullptr
+  V4<R>* out_hpos;        // [path] w = Hit.Distance
+  V4<R>* out_hnrm;        // [path] w = hit code
+  const uint32_t* queue;  // live path ids, or nullptr for the identity queue (bounce 0)
+  const uint32_t* count;  // number of queue entries
+  Control* ctl;
+};
+
 // trace: persistent warps, one ray per lane, scheduled warp-synchronously. On sm_70+ a per-lane `while` nest is not
 // re-converged at loop exits and degenerates into lanes issuing one at a time, so the kernel is written as ONE
 // warp-uniform loop whose every iteration runs exactly one of three bodies, chosen by warp vote:
@@ -758,10 +827,8 @@ __device__ __forceinline__ void stack_pop(const uint32_t* stack_node, const R* s
 }
 
 template <typename R, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinBlocks) k_trace(SceneView<R> sc, PathView<R> pv, int q, int prev,
-                                                                           int cur_buf, int identity_queue) {
-  const uint32_t count = pv.ctl->count[q];
-  const uint32_t* queue = pv.queue[q];
+__global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinBlocks) k_trace(SceneView<R> sc, TraceIO<R> io) {
+  const uint32_t count = *io.count;
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   uint32_t n_nodes = 0, n_prims = 0;
@@ -774,14 +841,15 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
   V3<R> o = mk3(R(0), R(0), R(0)), d = o, inv = o, oinv = o;
   uint32_t sgn = 0;
   Skip<R> sk;
-  sk.slot = REF_SLOT_MASK + 1;
-  sk.inside = false;
-  sk.hpos = sk.hnrm = sk.spos = nullptr;
+  sk.code = HIT_MISS;
+  SkipSrc<R> src;
+  src.hpos = io.in_hpos;
+  src.hnrm = io.in_hnrm;
+  src.spos = io.skip_pos;
   Best<R> best;
   best.t = Num<R>::inf();
   best.near_ = 0;
-  best.ref = kNone;
-  best.which = 0;
+  best.code = HIT_MISS;
   int sp = 0;
   uint32_t cur = kNone;
   R cur_near = 0;
@@ -792,9 +860,9 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
       // ---- refill ------------------------------------------------------------------------------------------
       if (finished) {  // (distance, slot | inside | which): position and normal are completed by finalize_hit in k_shade
         R w;
-        set_code(w, best.ref == kNone ? HIT_MISS : ((best.ref & REF_SLOT_MASK) | (best.which & 2 ? HIT_INSIDE : 0u) | (best.which & 1 ? HIT_SECOND : 0u)));
-        st4(&pv.hpos[cur_buf][path], R(0), R(0), R(0), best.t);
-        st4(&pv.hnrm[cur_buf][path], R(0), R(0), R(0), w);
+        set_code(w, best.code);
+        st4(&io.out_hpos[path], R(0), R(0), R(0), best.t);
+        st4(&io.out_hnrm[path], R(0), R(0), R(0), w);
         finished = false;
       }
       if (exhausted) {
@@ -803,17 +871,17 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
       }
       uint32_t base = 0;
       const int leader = __ffs(m_idle) - 1;
-      if (lane == leader) base = atomicAdd(&pv.ctl->work_trace, (uint32_t)__popc(m_idle));
+      if (lane == leader) base = atomicAdd(&io.ctl->work_trace, (uint32_t)__popc(m_idle));
       base = __shfl_sync(0xFFFFFFFFu, base, leader);
       bool got = true;
       if (!active) {
         const uint32_t idx = base + __popc(m_idle & lt_mask);
         got = idx < count;
         if (got) {
-          path = identity_queue ? idx : queue[idx];
-          V4<R> dv = ld4(&pv.dir[path]);
-          V4<R> op = ld4(&pv.hpos[prev][path]);
-          const uint32_t code = code_of(pv.hnrm[prev][path].w);
+          path = io.queue ? io.queue[idx] : idx;
+          V4<R> dv = ld4(&io.dir[path]);
+          V4<R> op = ld4(&io.in_hpos[path]);
+          const uint32_t code = code_of(io.in_hnrm[path].w);
           o = xyz(op);
           d = xyz(dv);
           if constexpr (Num<R>::is_f64)
@@ -825,15 +893,10 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
             oinv = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
             sgn = (rsignbit(d.x) ? 1u : 0u) | (rsignbit(d.y) ? 2u : 0u) | (rsignbit(d.z) ? 4u : 0u);
           }
-          sk.slot = (code == HIT_MISS) ? (REF_SLOT_MASK + 1) : (code & REF_SLOT_MASK);
-          sk.inside = (code & HIT_INSIDE) != 0;
-          sk.hpos = &pv.hpos[prev][path];
-          sk.hnrm = &pv.hnrm[prev][path];
-          sk.spos = pv.skip_pos ? &pv.skip_pos[path] : nullptr;
+          sk.code = code;
           best.t = Num<R>::inf();
           best.near_ = 0;
-          best.ref = kNone;
-          best.which = 0;
+          best.code = HIT_MISS;
           sp = 0;
           cur = sc.root;
           cur_near = 0;
@@ -919,7 +982,7 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
       // ---- leaf step ---------------------------------------------------------------------------------------
       if (active && (cur & REF_LEAF)) {
         if (COUNT) n_prims++;
-        test_leaf<R>(sc, cur, cur_near, o, d, sk, best);
+        test_leaf<R>(sc, cur, load_prim(sc, cur & REF_SLOT_MASK), cur_near, o, d, sk, src, path, best);
         stack_pop<R>(stack_node, stack_near, sp, best.t, cur, cur_near);
       }
     }
@@ -929,8 +992,8 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
     }
   }
   if (COUNT) {
-    atomicAdd(&pv.ctl->nodes_visited, (unsigned long long)n_nodes);
-    atomicAdd(&pv.ctl->prims_tested, (unsigned long long)n_prims);
+    atomicAdd(&io.ctl->nodes_visited, (unsigned long long)n_nodes);
+    atomicAdd(&io.ctl->prims_tested, (unsigned long long)n_prims);
   }
 }
 
@@ -958,30 +1021,55 @@ __device__ __forceinline__ float qbyte(uint32_t w, int k) {  // float(2^23 + byt
 #endif
 }
 
+#ifdef RTC_TRACE_MAXNREG  // tuning: an explicit register budget instead of one derived from the resident-CTA target
+#define RTC_Q8_BOUNDS __maxnreg__(RTC_TRACE_MAXNREG)
+#else
+#define RTC_Q8_BOUNDS __launch_bounds__(kTraceThreads, kTraceMinBlocks)
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(SceneView<float> sc, PathView<float> pv, int q, int prev,
-                                                                             int cur_buf, int identity_queue) {
+__global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io) {
   using R = float;
-  __shared__ uint2 s_stack[kQStack][kTraceThreads];
-  const uint32_t count = pv.ctl->count[q];
-  const uint32_t* queue = pv.queue[q];
-  const int lane = threadIdx.x & 31;
-  const int tid = threadIdx.x;
-  const uint32_t lt_mask = (1u << lane) - 1u;
+  extern __shared__ uint2 s_stack[];  // [sc.q_stack][kTraceThreads], then the per-lane cold state (RTC_Q8_SMEM_STATE)
+#if RTC_Q8_SMEM_STATE
+  // Ray state that only the leaf and refill bodies read (direction, path id, skip code) lives in shared memory: five
+  // registers fewer across the node step, which is what bounds the number of resident warps.
+  // (indexed off the extern array every time: 32-bit shared-window addresses, no generic pointers held in registers)
+#define RTC_SW(k) (reinterpret_cast<uint32_t*>(s_stack)[(2 * sc.q_stack + (k)) * kTraceThreads + threadIdx.x])
+#define RTC_D() mk3(__uint_as_float(RTC_SW(0)), __uint_as_float(RTC_SW(1)), __uint_as_float(RTC_SW(2)))
+#define RTC_PATH() RTC_SW(3)
+#define RTC_SKIP() RTC_SW(4)
+#else
+#define RTC_D() d
+#define RTC_PATH() path
+#define RTC_SKIP() sk.code
+#endif
+  const uint32_t count = *io.count;
+#define RTC_LANE() ((int)(threadIdx.x & 31))
   uint32_t n_nodes = 0, n_prims = 0, n_node_steps = 0, n_leaf_steps = 0;
   bool active = false, finished = false, exhausted = false;
+#if !RTC_Q8_SMEM_STATE
   uint32_t path = 0;
-  V3<R> o = mk3(0.f, 0.f, 0.f), d = o, inv = o;
-  uint32_t octinv = 0;
+  V3<R> d = mk3(0.f, 0.f, 0.f);
   Skip<R> sk;
-  sk.slot = REF_SLOT_MASK + 1;
-  sk.inside = false;
-  sk.hpos = sk.hnrm = sk.spos = nullptr;
+  sk.code = HIT_MISS;
+#endif
+#if RTC_Q8_SMEM_STATE < 2
+  V3<R> o = mk3(0.f, 0.f, 0.f), inv = o;
+#define RTC_O() o
+#define RTC_INV() inv
+#else  // origin and reciprocal direction too: read back at the top of each node / leaf body
+#define RTC_O() mk3(__uint_as_float(RTC_SW(5)), __uint_as_float(RTC_SW(6)), __uint_as_float(RTC_SW(7)))
+#define RTC_INV() mk3(__uint_as_float(RTC_SW(8)), __uint_as_float(RTC_SW(9)), __uint_as_float(RTC_SW(10)))
+#endif
+  uint32_t octinv = 0;
+  SkipSrc<R> src;
+  src.hpos = io.in_hpos;
+  src.hnrm = io.in_hnrm;
+  src.spos = io.skip_pos;
   Best<R> best;
   best.t = Num<R>::inf();
   best.near_ = 0;
-  best.ref = kNone;
-  best.which = 0;
+  best.code = HIT_MISS;
   int sp = 0;
   // current groups: inner (igx = child_base, igy = hits << 8 | imask) and leaf (lgx = prim_base, lgy = hits << 8 | lmask);
   // hit bits are stored at position slot ^ octinv so that the highest set bit is the child to visit first
@@ -993,9 +1081,10 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
       // ---- refill ------------------------------------------------------------------------------------------
       if (finished) {  // (distance, slot | inside | which): position and normal are completed by finalize_hit in k_shade
         R w;
-        set_code(w, best.ref == kNone ? HIT_MISS : ((best.ref & REF_SLOT_MASK) | (best.which & 2 ? HIT_INSIDE : 0u) | (best.which & 1 ? HIT_SECOND : 0u)));
-        st4(&pv.hpos[cur_buf][path], R(0), R(0), R(0), best.t);
-        st4(&pv.hnrm[cur_buf][path], R(0), R(0), R(0), w);
+        set_code(w, best.code);
+        const uint32_t fpath = RTC_PATH();
+        st4(&io.out_hpos[fpath], R(0), R(0), R(0), best.t);
+        st4(&io.out_hnrm[fpath], R(0), R(0), R(0), w);
         finished = false;
       }
       if (exhausted) {
@@ -1004,40 +1093,65 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
       }
       uint32_t base = 0;
       const int leader = __ffs(m_idle) - 1;
-      if (lane == leader) base = atomicAdd(&pv.ctl->work_trace, (uint32_t)__popc(m_idle));
+      if (RTC_LANE() == leader) base = atomicAdd(&io.ctl->work_trace, (uint32_t)__popc(m_idle));
       base = __shfl_sync(0xFFFFFFFFu, base, leader);
       bool got = true;
       if (!active) {
-        const uint32_t idx = base + __popc(m_idle & lt_mask);
+        const uint32_t idx = base + __popc(m_idle & ((1u << RTC_LANE()) - 1u));
         got = idx < count;
         if (got) {
-          path = identity_queue ? idx : queue[idx];
-          V4<R> dv = ld4(&pv.dir[path]);
-          V4<R> op = ld4(&pv.hpos[prev][path]);
-          const uint32_t code = code_of(pv.hnrm[prev][path].w);
+          const uint32_t npath = io.queue ? io.queue[idx] : idx;
+          V4<R> dv = ld4(&io.dir[npath]);
+          V4<R> op = ld4(&io.in_hpos[npath]);
+          const uint32_t code = code_of(io.in_hnrm[npath].w);
+#if RTC_Q8_SMEM_STATE < 2
           o = xyz(op);
+#else
+          const V3<R> o = xyz(op);
+          RTC_SW(5) = __float_as_uint(o.x);
+          RTC_SW(6) = __float_as_uint(o.y);
+          RTC_SW(7) = __float_as_uint(o.z);
+#endif
+#if RTC_Q8_SMEM_STATE
+          const V3<R> d = xyz(dv);
+          RTC_SW(0) = __float_as_uint(d.x);
+          RTC_SW(1) = __float_as_uint(d.y);
+          RTC_SW(2) = __float_as_uint(d.z);
+          RTC_PATH() = npath;
+          RTC_SKIP() = code;
+          Skip<R> sk;
+          sk.code = code;
+#else
           d = xyz(dv);
+          path = npath;
+          sk.code = code;
+#endif
+#if RTC_Q8_SMEM_STATE < 2
           inv = mk3(clamped_rcp(d.x), clamped_rcp(d.y), clamped_rcp(d.z));
+#else
+          const V3<R> inv = mk3(clamped_rcp(d.x), clamped_rcp(d.y), clamped_rcp(d.z));
+          RTC_SW(8) = __float_as_uint(inv.x);
+          RTC_SW(9) = __float_as_uint(inv.y);
+          RTC_SW(10) = __float_as_uint(inv.z);
+#endif
           const uint32_t oct = (rsignbit(d.x) ? 1u : 0u) | (rsignbit(d.y) ? 2u : 0u) | (rsignbit(d.z) ? 4u : 0u);
           octinv = 7u ^ oct;
-          sk.slot = (code == HIT_MISS) ? (REF_SLOT_MASK + 1) : (code & REF_SLOT_MASK);
-          sk.inside = (code & HIT_INSIDE) != 0;
-          sk.hpos = &pv.hpos[prev][path];
-          sk.hnrm = &pv.hnrm[prev][path];
-          sk.spos = pv.skip_pos ? &pv.skip_pos[path] : nullptr;
           best.t = Num<R>::inf();
           best.near_ = 0;
-          best.ref = kNone;
-          best.which = 0;
+          best.code = HIT_MISS;
           sp = 0;
+          // a ray with a non-finite component (a degenerate bounce) hits nothing; without this guard its NaN slab
+          // distances would pass every box test and walk the whole tree
+          const bool finite = (fabsf(o.x) + fabsf(o.y) + fabsf(o.z)) + (fabsf(d.x) + fabsf(d.y) + fabsf(d.z)) < Num<R>::inf();
           // primitives without a finite box (planes) are tested up front, in leaf order
-          for (int i = 0; i < sc.n_unbounded; i++) {
+          for (int i = 0; finite && i < sc.n_unbounded; i++) {
             if (COUNT) n_prims++;
-            test_leaf<R>(sc, sc.unbounded[i], -Num<R>::inf(), o, d, sk, best);
+            const uint32_t uref = sc.unbounded[i];
+            test_leaf<R>(sc, uref, load_prim(sc, uref & REF_SLOT_MASK), -Num<R>::inf(), o, d, sk, src, npath, best);
           }
           // virtual root group: one inner child in slot 0 = node 0
           igx = 0;
-          igy = sc.qnodes ? (((1u << (0u ^ octinv)) << 8) | 1u) : 0u;
+          igy = (sc.qnodes && finite) ? (((1u << (0u ^ octinv)) << 8) | 1u) : 0u;
           lgx = 0;
           lgy = 0;
           active = true;
@@ -1057,7 +1171,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
     if (__popc(m_node) >= __popc(m_leaf) && m_node) {
 #endif
       // ---- node step ---------------------------------------------------------------------------------------
-      if (COUNT && lane == 0) n_node_steps++;
+      if (COUNT && RTC_LANE() == 0) n_node_steps++;
       if (want_node) {
         const uint32_t hits = igy >> 8;
         const uint32_t b = 31u - (uint32_t)__clz((int)hits);
@@ -1066,7 +1180,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
         const uint32_t node = igx + (uint32_t)__popc(imask_g & ((1u << s) - 1u));
         igy &= ~(0x100u << b);
         if ((igy >> 8) != 0) {  // siblings still pending: the group goes to the stack
-          s_stack[sp][tid] = make_uint2(igx, igy);
+          s_stack[sp * kTraceThreads + threadIdx.x] = make_uint2(igx, igy);
           sp++;
         }
         const CNode* np = sc.qnodes + node;
@@ -1081,12 +1195,13 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
         const uint32_t imask = em >> 24, lmask = w0[6] & 0xFFu;
         // t = (p + q * step - o) * inv = q * (step * inv) + (p - o) * inv ; q enters as 2^23 + q, so the addend carries
         // -2^23 * step * inv (its rounding is half a grid step: the builder pads every box by one step)
-        const float ax = sx * inv.x, ay = sy * inv.y, az = sz * inv.z;
-        const float bx = fmaf(-8388608.0f, ax, (__uint_as_float(w0[0]) - o.x) * inv.x);
-        const float by = fmaf(-8388608.0f, ay, (__uint_as_float(w0[1]) - o.y) * inv.y);
-        const float bz = fmaf(-8388608.0f, az, (__uint_as_float(w0[2]) - o.z) * inv.z);
+        const V3<R> ro = RTC_O(), ri = RTC_INV();
+        const float ax = sx * ri.x, ay = sy * ri.y, az = sz * ri.z;
+        const float bx = fmaf(-8388608.0f, ax, (__uint_as_float(w0[0]) - ro.x) * ri.x);
+        const float by = fmaf(-8388608.0f, ay, (__uint_as_float(w0[1]) - ro.y) * ri.y);
+        const float bz = fmaf(-8388608.0f, az, (__uint_as_float(w0[2]) - ro.z) * ri.z);
         // near / far byte rows by direction sign: w1 = {lox0,lox1,loy0,loy1,loz0,loz1,hix0,hix1}, w2 = {hiy0,hiy1,hiz0,hiz1}
-        const bool nx_ = inv.x < 0.0f, ny_ = inv.y < 0.0f, nz_ = inv.z < 0.0f;
+        const bool nx_ = !(octinv & 1u), ny_ = !(octinv & 2u), nz_ = !(octinv & 4u);  // sign of the direction per axis
         const uint32_t nxw[2] = {nx_ ? w1[6] : w1[0], nx_ ? w1[7] : w1[1]}, fxw[2] = {nx_ ? w1[0] : w1[6], nx_ ? w1[1] : w1[7]};
         const uint32_t nyw[2] = {ny_ ? w2.x : w1[2], ny_ ? w2.y : w1[3]}, fyw[2] = {ny_ ? w1[2] : w2.x, ny_ ? w1[3] : w2.y};
         const uint32_t nzw[2] = {nz_ ? w2.z : w1[4], nz_ ? w2.w : w1[5]}, fzw[2] = {nz_ ? w1[4] : w2.z, nz_ ? w1[5] : w2.w};
@@ -1113,7 +1228,7 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
       }
     } else {
       // ---- leaf step ---------------------------------------------------------------------------------------
-      if (COUNT && lane == 0) n_leaf_steps++;
+      if (COUNT && RTC_LANE() == 0) n_leaf_steps++;
       if (want_leaf) {
         const uint32_t hits = lgy >> 8;
         const uint32_t b = 31u - (uint32_t)__clz((int)hits);
@@ -1121,13 +1236,18 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
         const uint32_t slot = lgx + (uint32_t)__popc((lgy & 0xFFu) & ((1u << s) - 1u));
         lgy &= ~(0x100u << b);
         if (COUNT) n_prims++;
-        test_leaf<R>(sc, __ldg(&sc.prim_ref[slot]), R(0), o, d, sk, best);
+        const PrimRec<R> pr = load_prim(sc, slot);
+#if RTC_Q8_SMEM_STATE
+        Skip<R> sk;
+        sk.code = RTC_SKIP();
+#endif
+        test_leaf<R>(sc, ref_of(pr), pr, R(0), RTC_O(), RTC_D(), sk, src, RTC_PATH(), best);
       }
     }
     if (active && (lgy >> 8) == 0 && (igy >> 8) == 0) {
       if (sp > 0) {
         sp--;
-        const uint2 g = s_stack[sp][tid];
+        const uint2 g = s_stack[sp * kTraceThreads + threadIdx.x];
         igx = g.x;
         igy = g.y;
       } else {
@@ -1136,14 +1256,21 @@ __global__ void __launch_bounds__(kTraceThreads, kTraceMinBlocks) k_trace_q8(Sce
       }
     }
   }
+#undef RTC_O
+#undef RTC_INV
+#undef RTC_SW
+#undef RTC_D
+#undef RTC_PATH
+#undef RTC_SKIP
   if (COUNT) {
-    atomicAdd(&pv.ctl->nodes_visited, (unsigned long long)n_nodes);
-    atomicAdd(&pv.ctl->prims_tested, (unsigned long long)n_prims);
-    if (lane == 0) {
-      atomicAdd(&pv.ctl->node_steps, (unsigned long long)n_node_steps);
-      atomicAdd(&pv.ctl->leaf_steps, (unsigned long long)n_leaf_steps);
+    atomicAdd(&io.ctl->nodes_visited, (unsigned long long)n_nodes);
+    atomicAdd(&io.ctl->prims_tested, (unsigned long long)n_prims);
+    if (RTC_LANE() == 0) {
+      atomicAdd(&io.ctl->node_steps, (unsigned long long)n_node_steps);
+      atomicAdd(&io.ctl->leaf_steps, (unsigned long long)n_leaf_steps);
     }
   }
+#undef RTC_LANE
 }
 
 // DoubleColor.Luminance (DoubleColor.cs:76-81)
@@ -1496,12 +1623,12 @@ __global__ void __launch_bounds__(kStreamThreads) k_overlay_prims(SceneView<R> s
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 template <typename R>
-int Kernels<R>::trace_blocks_per_sm() {
+int Kernels<R>::trace_blocks_per_sm(size_t smem) {
   int nb = 0;
   if constexpr (Num<R>::is_f64)
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<R, false>, kTraceThreads, 0);
   else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_q8<false>, kTraceThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_q8<false>, kTraceThreads, smem);
   return nb > 0 ? nb : 1;
 }
 
@@ -1523,18 +1650,34 @@ cudaError_t Kernels<R>::camera_rays(const LaunchCfg& cfg, const CameraView<R>& c
 template <typename R>
 cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, int prev, int cur,
                               bool identity_queue) {
-  static int per_sm = trace_blocks_per_sm();
+  const size_t smem = Num<R>::is_f64 ? 0 : (size_t)sc.q_stack * kTraceThreads * sizeof(uint2) + (RTC_Q8_SMEM_STATE >= 2 ? 11 : RTC_Q8_SMEM_STATE ? 5 : 0) * kTraceThreads * sizeof(float);
+  static thread_local size_t per_sm_smem = ~(size_t)0;  // resident CTAs per SM for the stack size last seen (persistent grid = all of them)
+  static thread_local int per_sm = 1;
+  if (smem != per_sm_smem) {
+    per_sm = trace_blocks_per_sm(smem);
+    per_sm_smem = smem;
+  }
   int grid = cfg.sm_count * per_sm;
+  TraceIO<R> io;
+  io.dir = pv.dir;
+  io.in_hpos = pv.hpos[prev];
+  io.in_hnrm = pv.hnrm[prev];
+  io.skip_pos = pv.skip_pos;
+  io.out_hpos = pv.hpos[cur];
+  io.out_hnrm = pv.hnrm[cur];
+  io.queue = identity_queue ? nullptr : pv.queue[q];
+  io.count = &pv.ctl->count[q];
+  io.ctl = pv.ctl;
   if constexpr (Num<R>::is_f64) {
     if (cfg.counters)
-      k_trace<R, true><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+      k_trace<R, true><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, io);
     else
-      k_trace<R, false><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+      k_trace<R, false><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, io);
   } else {
     if (cfg.counters)
-      k_trace_q8<true><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+      k_trace_q8<true><<<grid, kTraceThreads, smem, cfg.stream>>>(sc, io);
     else
-      k_trace_q8<false><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, pv, q, prev, cur, identity_queue ? 1 : 0);
+      k_trace_q8<false><<<grid, kTraceThreads, smem, cfg.stream>>>(sc, io);
   }
   return cudaGetLastError();
 }

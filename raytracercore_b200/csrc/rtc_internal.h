@@ -5,9 +5,11 @@
 //   DNode<R>  W children per node (W = 4 in f32 mode: 128 B = one cache line; W = 2 in f64 mode: 128 B), stored as
 //             lo[axis][child] / hi[axis][child] rows + W child references, so one 16-byte load = one bound of 4 children.
 //   DPrim<R>  3 x V4 per primitive, stored in left-first DFS leaf order so slot == leaf order (tie-break key):
-//               triangle  a=(v0.xyz,N.x) b=(e1.xyz,N.y) c=(e2.xyz,N.z)      (Triangle.cs:22-29)
-//               sphere    a=(center.xyz,radius)                              (Sphere.cs:11-14)
-//               plane     a=(normal.xyz,originDistance)                      (Plane.cs:13-14)
+//               triangle  a=(v0.xyz,N.x) b=(e1.xyz,N.y) c=(e2.xyz,ref)      (Triangle.cs:22-29; N.z lives in prim_nz[])
+//               sphere    a=(center.xyz,radius)            c=(0,0,0,ref)     (Sphere.cs:11-14)
+//               plane     a=(normal.xyz,originDistance)    c=(0,0,0,ref)     (Plane.cs:13-14)
+//             ref = the leaf reference (REF_LEAF | kind | flags | slot) as raw bits in the w lane, so that a leaf test is
+//             ONE memory round trip (three 16-byte loads issued together) instead of reference -> record.
 //   DXform<R> 9 x V4 for transformed spheres (rows 0-2 of MatrixToWorld, MatrixToObject, MatrixToNormal) or
 //             vertex-normal triangles (n0,n1,n2 in rows 0-2).
 //   DMat<R>   4 x V4: (emission, ior) (diffuse, shininess) (specular, 0) (refraction, 0)  (Primitive.cs:16-129)
@@ -86,7 +88,10 @@ struct alignas(32) CNode {
   uint32_t pad1[4];
 };
 static_assert(sizeof(CNode) == 96, "CNode layout");
-constexpr int kQStack = 24;  // shared-memory traversal stack entries per lane for the 8-wide tree
+// The 8-wide traversal stack lives in dynamic shared memory, [entry][thread] x 8 bytes, sized per scene to the tree's
+// depth + 1 (one pending sibling group per level): a 1 M-triangle tree needs ~10 entries = 10 KB per 128-thread CTA,
+// which leaves most of the SM's 228 KB to the L1 cache the node and primitive fetches run through.
+constexpr int kQStackMax = 48;
 
 template <typename R>
 struct DPrim {
@@ -111,12 +116,14 @@ struct SceneView {
   const DMat<R>* mats;
   const int32_t* aux;      // per slot: xform row (low 30 bits) | REF_VNORMALS_AUX, or -1
   const int32_t* prim_id;  // per slot: Primitive.ID
-  const uint32_t* prim_ref;  // per slot: the leaf reference (kind + flags + slot)
+  const R* prim_nz;        // per slot: z of the triangle's face normal (x, y sit in the record's w lanes); only
+                           // finalize_hit reads it
   uint32_t root;           // index of the root inner node
   int32_t n_prims;
   const CNode* qnodes;     // f32 mode only: the quantised 8-wide tree over the bounded primitives
   const uint32_t* unbounded;  // f32 mode only: leaf references of primitives with infinite boxes (planes)
   int32_t n_unbounded;
+  int32_t q_stack;         // f32 mode only: traversal stack entries per lane (tree depth + 1)
 };
 
 template <typename R>
@@ -199,7 +206,7 @@ struct Kernels {
                                   const PathView<R>& pv);
   static cudaError_t overlay_prims(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,
                                    const PathView<R>& pv, int cur, int32_t* out);
-  static int trace_blocks_per_sm();
+  static int trace_blocks_per_sm(size_t smem);
 };
 
 // BVH.GetIntersectionCount per pixel over the reference-shaped (binary, f64) tree; f64 arithmetic in both modes.
