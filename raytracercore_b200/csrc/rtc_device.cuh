@@ -8,6 +8,8 @@
 #pragma once
 #include <math_constants.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "rtc_internal.h"
@@ -334,12 +336,15 @@ __device__ __forceinline__ int tri_hits(const SceneView<R>& sc, uint32_t ref, co
   return 1;
 }
 
-// Sphere.RayTraceAVX (Primitives/Sphere.cs:50-155). `x` = the sphere's matrix rows when it is transformed, else nullptr.
-template <typename R, bool WITH_NORMAL, bool FORCE = false>
+// Sphere.RayTraceAVX (Primitives/Sphere.cs:50-155). XF = the sphere is transformed and `x` holds its matrix rows. XF is a
+// template parameter so that the rows are defined and consumed inside one straight-line region: a run-time flag tested
+// twice makes them conditionally defined, and the register allocator then keeps all of them alive around the whole
+// traversal loop (24 registers).
+template <typename R, bool WITH_NORMAL, bool FORCE, bool XF>
 __device__ __forceinline__ int sphere_hits(const DXform<R>* x, const V4<R>& A, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
   V3<R> C = xyz(A);
   R radius = A.w;
-  const bool xf = x != nullptr;
+  constexpr bool xf = XF;
   V3<R> oo = o, od = d;
   V4<R> rows[9];
   if (xf) {  // :58-76
@@ -484,8 +489,8 @@ __device__ __forceinline__ int prim_hits(const SceneView<R>& sc, uint32_t ref, c
   if (kind == DK_TRI) return tri_hits<R, WITH_NORMAL, FORCE>(sc, ref, p.a, p.b, p.c, o, d, out, forced_inside);
   if (kind == DK_PLANE) return plane_hits<R, WITH_NORMAL, FORCE>(p.a, o, d, out);
   if (kind == DK_XSPHERE)
-    return sphere_hits<R, WITH_NORMAL, FORCE>(sc.xforms + sc.aux[ref & REF_SLOT_MASK], p.a, o, d, out);
-  return sphere_hits<R, WITH_NORMAL, FORCE>(nullptr, p.a, o, d, out);
+    return sphere_hits<R, WITH_NORMAL, FORCE, true>(sc.xforms + sc.aux[ref & REF_SLOT_MASK], p.a, o, d, out);
+  return sphere_hits<R, WITH_NORMAL, FORCE, false>(nullptr, p.a, o, d, out);
 }
 
 // The skip hit (previous bounce's Hit) as the trace kernel sees it: primitive slot and inside flag live in
@@ -727,7 +732,7 @@ constexpr int kStreamThreads = 256;
 #define RTC_TRACE_THREADS 128
 #endif
 #ifndef RTC_TRACE_MIN_BLOCKS
-#define RTC_TRACE_MIN_BLOCKS 5
+#define RTC_TRACE_MIN_BLOCKS 7
 #endif
 #ifndef RTC_Q8_PRMT
 #define RTC_Q8_PRMT 0
@@ -737,6 +742,12 @@ constexpr int kStreamThreads = 256;
 #endif
 #ifndef RTC_Q8_SMEM_STATE
 #define RTC_Q8_SMEM_STATE 1
+#endif
+#ifndef RTC_Q8_PACKED
+#define RTC_Q8_PACKED 1
+#endif
+#ifndef RTC_Q8_SIGNFOLD
+#define RTC_Q8_SIGNFOLD 0
 #endif
 constexpr int kTraceThreads = RTC_TRACE_THREADS;
 constexpr int kTraceMinBlocks = RTC_TRACE_MIN_BLOCKS;
@@ -1026,6 +1037,23 @@ __device__ __forceinline__ float qbyte(uint32_t w, int k) {  // float(2^23 + byt
 #else
 #define RTC_Q8_BOUNDS __launch_bounds__(kTraceThreads, kTraceMinBlocks)
 #endif
+// Packed f32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two children's slab distances.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  unsigned long long A, B, C, D;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(C) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(C));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
+}
+__device__ __forceinline__ void fsub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  unsigned long long A, B, D;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
+}
+
 template <bool COUNT>
 __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io) {
   using R = float;
@@ -1205,6 +1233,47 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         const uint32_t nxw[2] = {nx_ ? w1[6] : w1[0], nx_ ? w1[7] : w1[1]}, fxw[2] = {nx_ ? w1[0] : w1[6], nx_ ? w1[1] : w1[7]};
         const uint32_t nyw[2] = {ny_ ? w2.x : w1[2], ny_ ? w2.y : w1[3]}, fyw[2] = {ny_ ? w1[2] : w2.x, ny_ ? w1[3] : w2.y};
         const uint32_t nzw[2] = {nz_ ? w2.z : w1[4], nz_ ? w2.w : w1[5]}, fzw[2] = {nz_ ? w1[4] : w2.z, nz_ ? w1[5] : w2.w};
+#if RTC_Q8_PACKED
+        // two children per FFMA2; the hit mask is gathered from the sign bits of (far - near) with one funnel shift per
+        // child, which leaves child c at bit 7 - c = c ^ 7: the octant permutation below absorbs the reversal
+        uint32_t acc = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          const int wi = c >> 2, k = c & 3;
+          float tnx0, tnx1, tny0, tny1, tnz0, tnz1, tfx0, tfx1, tfy0, tfy1, tfz0, tfz1;
+          ffma2(tnx0, tnx1, qbyte(nxw[wi], k), qbyte(nxw[wi], k + 1), ax, bx);
+          ffma2(tny0, tny1, qbyte(nyw[wi], k), qbyte(nyw[wi], k + 1), ay, by);
+          ffma2(tnz0, tnz1, qbyte(nzw[wi], k), qbyte(nzw[wi], k + 1), az, bz);
+          ffma2(tfx0, tfx1, qbyte(fxw[wi], k), qbyte(fxw[wi], k + 1), ax, bx);
+          ffma2(tfy0, tfy1, qbyte(fyw[wi], k), qbyte(fyw[wi], k + 1), ay, by);
+          ffma2(tfz0, tfz1, qbyte(fzw[wi], k), qbyte(fzw[wi], k + 1), az, bz);
+#if RTC_Q8_SIGNFOLD
+          // max(near, 0) <= min(far, best) <=> none of (far - near), far, (best - near) is negative: one OR of sign bits
+          const float nr0 = fmaxf(fmaxf(tnx0, tny0), tnz0), nr1 = fmaxf(fmaxf(tnx1, tny1), tnz1);
+          const float fr0 = fminf(fminf(tfx0, tfy0), tfz0), fr1 = fminf(fminf(tfx1, tfy1), tfz1);
+          float df0, df1, db0, db1;
+          fsub2(df0, df1, fr0, fr1, nr0, nr1);
+          fsub2(db0, db1, best.t, best.t, nr0, nr1);
+          acc = __funnelshift_l(__float_as_uint(df0) | __float_as_uint(fr0) | __float_as_uint(db0), acc, 1);
+          acc = __funnelshift_l(__float_as_uint(df1) | __float_as_uint(fr1) | __float_as_uint(db1), acc, 1);
+#else
+          const float nr0 = fmaxf(fmaxf(fmaxf(tnx0, tny0), tnz0), 0.0f), nr1 = fmaxf(fmaxf(fmaxf(tnx1, tny1), tnz1), 0.0f);
+          const float fr0 = fminf(fminf(fminf(tfx0, tfy0), tfz0), best.t), fr1 = fminf(fminf(fminf(tfx1, tfy1), tfz1), best.t);
+          float df0, df1;
+          fsub2(df0, df1, fr0, fr1, nr0, nr1);  // negative <=> near > far (x - x = +0; no NaN: every term is finite)
+          acc = __funnelshift_l(__float_as_uint(df0), acc, 1);
+          acc = __funnelshift_l(__float_as_uint(df1), acc, 1);
+#endif
+        }
+        const uint32_t hitrev = ~acc & 0xFFu;  // bit 7 - c set <=> child c is hit
+        const uint32_t imrev = __brev(imask) >> 24, lmrev = __brev(lmask) >> 24;
+        uint32_t hb = (hitrev & imrev) | ((hitrev & lmrev) << 8);
+        // reversed slot order -> visit order: bit (s ^ 7) moves to position s ^ octinv, i.e. an xor by (octinv ^ 7)
+        const uint32_t px = octinv ^ 7u;
+        if (px & 4u) hb = ((hb & 0x0F0Fu) << 4) | ((hb >> 4) & 0x0F0Fu);
+        if (px & 2u) hb = ((hb & 0x3333u) << 2) | ((hb >> 2) & 0x3333u);
+        if (px & 1u) hb = ((hb & 0x5555u) << 1) | ((hb >> 1) & 0x5555u);
+#else
         uint32_t hitbits = 0;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
@@ -1221,6 +1290,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         if (octinv & 4u) hb = ((hb & 0x0F0Fu) << 4) | ((hb >> 4) & 0x0F0Fu);
         if (octinv & 2u) hb = ((hb & 0x3333u) << 2) | ((hb >> 2) & 0x3333u);
         if (octinv & 1u) hb = ((hb & 0x5555u) << 1) | ((hb >> 1) & 0x5555u);
+#endif
         igx = w0[4];
         igy = ((hb & 0xFFu) << 8) | imask;
         lgx = w0[5];
@@ -1655,6 +1725,8 @@ cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, cons
   static thread_local int per_sm = 1;
   if (smem != per_sm_smem) {
     per_sm = trace_blocks_per_sm(smem);
+    if (const char* cap = std::getenv("RTC_TRACE_BLOCKS_PER_SM"))  // tuning aid: fewer resident CTAs than fit
+      per_sm = std::max(1, std::min(per_sm, std::atoi(cap)));
     per_sm_smem = smem;
   }
   int grid = cfg.sm_count * per_sm;
