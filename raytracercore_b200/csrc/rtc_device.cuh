@@ -40,8 +40,25 @@ __device__ __forceinline__ float rsqrt_(float a) { return sqrtf(a); }
 __device__ __forceinline__ double rsqrt_(double a) { return sqrt(a); }
 __device__ __forceinline__ float rrcp(float a) { return __frcp_rn(a); }
 __device__ __forceinline__ double rrcp(double a) { return 1.0 / a; }
+// Intersection arithmetic of the f32 mode: the hardware approximations (MUFU.RCP / MUFU.SQRT, <= 2 ulp), which have no
+// out-of-line slow path -- an IEEE division or square root compiles to a subroutine call whose calling convention
+// constrains register allocation around the whole traversal loop. f64 mode keeps the exact operations.
+__device__ __forceinline__ float xrcp(float a) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ double xrcp(double a) { return 1.0 / a; }
+__device__ __forceinline__ float xsqrt(float a) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ double xsqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ float xdiv(float a, float b) { return a * xrcp(b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return a / b; }
 __device__ __forceinline__ float clamped_rcp(float a) {
-  float r = __frcp_rn(a);
+  float r = xrcp(a);
   return fabsf(r) <= 0x1.0p64f ? r : copysignf(0x1.0p64f, a);  // also maps the NaN of 1/NaN away
 }
 __device__ __forceinline__ double clamped_rcp(double a) { return 1.0 / a; }
@@ -102,6 +119,11 @@ template <typename R>
 __device__ __forceinline__ V3<R> normalize3(const V3<R>& a) {
   R l = rsqrt_((a.x * a.x + a.y * a.y) + a.z * a.z);
   return mk3(a.x / l, a.y / l, a.z / l);
+}
+template <typename R>
+__device__ __forceinline__ V3<R> xnormalize3(const V3<R>& a) {  // the same with the intersection arithmetic
+  R l = xsqrt((a.x * a.x + a.y * a.y) + a.z * a.z);
+  return mk3(xdiv(a.x, l), xdiv(a.y, l), xdiv(a.z, l));
 }
 // Mat4x4D * Vec4D through SIMDHelpers.MultiplyMatrixVector (Mat4x4D.cs:171-180, SIMDHelpers.cs:111-127,222-237):
 // (m0 x + m1 y) + (m2 z + m3 w), for a point (w = 1) and for a direction (w = 0).
@@ -302,7 +324,7 @@ __device__ __forceinline__ int tri_hits(const SceneView<R>& sc, uint32_t ref, co
   R v = dot3(d, s1);
   R dist = dot3(e2, s1);
   R det = dot3(e1, s2);
-  R inv = rrcp(det);                 // :107
+  R inv = xrcp(det);                 // :107
   if (risnan(inv)) inv = 0;          // :108-110
   u = u * inv;                       // :112
   v = v * inv;
@@ -351,14 +373,14 @@ __device__ __forceinline__ int sphere_hits(const DXform<R>* x, const V4<R>& A, c
 #pragma unroll
     for (int i = 0; i < 9; i++) rows[i] = ldg4(&x->r[i]);
     oo = xf_point(rows, o);
-    od = normalize3(xf_dir(rows, d));
+    od = xnormalize3(xf_dir(rows, d));
   }
   V3<R> off = oo - C;  // :79
   R t_far, t_close;
   if constexpr (Num<R>::is_f64) {
     R b = -2 * dot3(off, od);                     // :80,84
     R c = dot3(off, off) - radius * radius;       // :81,85 (RadiusSqr = value*value, Sphere.cs:44-45)
-    R radix = rsqrt_((b * b) - (4 * c));          // :86
+    R radix = xsqrt((b * b) - (4 * c));          // :86
     t_far = (b + radix) / 2;                      // :89
     t_close = (b - radix) / 2;                    // :90
   } else {
@@ -368,10 +390,10 @@ __device__ __forceinline__ int sphere_hits(const DXform<R>* x, const V4<R>& A, c
     R disc = radius * radius - dot3(l, l);
     if (FORCE) disc = fmaxf(disc, R(0));  // an accepted grazing hit keeps a real root
     R c = dot3(off, off) - radius * radius;
-    R sq = rsqrt_(disc);  // NaN when the ray misses
+    R sq = xsqrt(disc);  // NaN when the ray misses
     const bool fwd = bp >= 0;  // (-0 counts as forward: q must not cancel)
     R q = fwd ? bp + sq : bp - sq;
-    R other = c / q;
+    R other = xdiv(c, q);
     if (fwd) {
       t_far = q;
       t_close = other;
@@ -386,15 +408,16 @@ __device__ __forceinline__ int sphere_hits(const DXform<R>* x, const V4<R>& A, c
   V3<R> pc = mk3(rfma(t_close, od.x, oo.x), rfma(t_close, od.y, oo.y), rfma(t_close, od.z, oo.z));  // :97
   V3<R> nf, nc;
   if (WITH_NORMAL || xf) {
-    nf = (pf - C) / radius;  // :95
-    nc = (pc - C) / radius;  // :98
+    const V3<R> df = pf - C, dc = pc - C;
+    nf = mk3(xdiv(df.x, radius), xdiv(df.y, radius), xdiv(df.z, radius));  // :95
+    nc = mk3(xdiv(dc.x, radius), xdiv(dc.y, radius), xdiv(dc.z, radius));  // :98
   }
   if (xf) {  // :100-139
     pf = xf_point(rows + 3, pf);
     pc = xf_point(rows + 3, pc);
     if (WITH_NORMAL) {
-      nf = normalize3(xf_dir(rows + 6, nf));
-      nc = normalize3(xf_dir(rows + 6, nc));
+      nf = xnormalize3(xf_dir(rows + 6, nf));
+      nc = xnormalize3(xf_dir(rows + 6, nc));
     }
     t_far = dot3(d, pf - o);
     t_close = dot3(d, pc - o);
@@ -432,7 +455,7 @@ __device__ __forceinline__ bool nearly_equal(R a, R b, R delta) {
   if constexpr (Num<R>::is_f64)
     return delta <= 4.94065645841247e-317 || delta / mx < 1e-24;  // double.Epsilon * 1e7 ; Util.NearEnough
   else
-    return delta / mx < 1e-9f;  // f32 stand-in for NearEnough (self-hit rule in float mode)
+    return xdiv(delta, mx) < 1e-9f;  // f32 stand-in for NearEnough (self-hit rule in float mode)
 }
 
 // Plane.DoRayTrace (Primitives/Plane.cs:36-66)
@@ -450,12 +473,12 @@ __device__ __forceinline__ int plane_hits(const V4<R>& A, const V3<R>& o, const 
     return 1;
   }
   if (!FORCE && denom == 0) return 0;  // :44-45
-  R dist = (od - ray_dist) / denom;  // :47
+  R dist = xdiv(od - ray_dist, denom);  // :47
   if (FORCE || dist >= (Num<R>::is_f64 ? R(-1e-24) : R(0))) {  // :49
     V3<R> hp = o + (d * dist);  // :51
     bool inside = dot3(N, d) > 0;  // :56
     V3<R> dl = hp - o;
-    out[0].t = rsqrt_((dl.x * dl.x + dl.y * dl.y) + dl.z * dl.z);  // :62 (hitPos - ray.Origin).Length
+    out[0].t = xsqrt((dl.x * dl.x + dl.y * dl.y) + dl.z * dl.z);  // :62 (hitPos - ray.Origin).Length
     if (with_pos<R, WITH_NORMAL>()) out[0].pos = hp;
     out[0].inside = inside;
     if (WITH_NORMAL) out[0].normal = inside ? neg3(N) : N;
@@ -512,9 +535,9 @@ struct SkipSrc {          // warp-uniform: where the skip records of the wavefro
 
 // Util.RayHitMatches (Util.cs:179-192) for a candidate on the same primitive as the skip hit.
 template <typename R>
-__device__ __noinline__ bool skip_matches(const SceneView<R>* scp, uint32_t ref, V3<R> o, V3<R> d, int which, bool cand_inside,
-                                          R cand_t, V3<R> cand_pos, bool skip_inside, const V4<R>* hpos, const V4<R>* hnrm,
-                                          const V4<R>* sposp) {
+__device__ __forceinline__ bool skip_matches_impl(const SceneView<R>* scp, uint32_t ref, V3<R> o, V3<R> d, int which, bool cand_inside,
+                                                  R cand_t, V3<R> cand_pos, bool skip_inside, const V4<R>* hpos, const V4<R>* hnrm,
+                                                  const V4<R>* sposp) {
   V4<R> hp = ld4(hpos), hn = ld4(hnrm);
   V3<R> spos = sposp ? xyz(ld4(sposp)) : xyz(hp);
   V3<R> snrm = xyz(hn);
@@ -536,6 +559,18 @@ __device__ __noinline__ bool skip_matches(const SceneView<R>* scp, uint32_t ref,
   if (!nearly_equal(la, lb, ld)) return false;
   if (dot3(d, snrm) > 0) return cand_inside != skip_inside;
   return cand_inside == skip_inside;
+}
+// f64: out of line (it re-evaluates the primitive with normals); f32: a dozen operations, inlined so that the traversal
+// kernel contains no call at all.
+static __device__ __noinline__ bool skip_matches(const SceneView<double>* scp, uint32_t ref, V3<double> o, V3<double> d, int which,
+                                          bool cand_inside, double cand_t, V3<double> cand_pos, bool skip_inside,
+                                          const V4<double>* hpos, const V4<double>* hnrm, const V4<double>* sposp) {
+  return skip_matches_impl<double>(scp, ref, o, d, which, cand_inside, cand_t, cand_pos, skip_inside, hpos, hnrm, sposp);
+}
+static __device__ __forceinline__ bool skip_matches(const SceneView<float>* scp, uint32_t ref, V3<float> o, V3<float> d, int which,
+                                             bool cand_inside, float cand_t, V3<float> cand_pos, bool skip_inside,
+                                             const V4<float>* hpos, const V4<float>* hnrm, const V4<float>* sposp) {
+  return skip_matches_impl<float>(scp, ref, o, d, which, cand_inside, cand_t, cand_pos, skip_inside, hpos, hnrm, sposp);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -612,7 +647,7 @@ __device__ __forceinline__ bool consider_cand(const SceneView<R>& sc, uint32_t r
       same = true;
     } else {
       const V3<R> cpos = Num<R>::is_f64 ? pos : o + (d * t);
-      same = skip_matches<R>(Num<R>::is_f64 ? &sc : nullptr, ref, o, d, which, inside, t, cpos, sk.inside(), src.hpos + path, src.hnrm + path,
+      same = skip_matches(Num<R>::is_f64 ? &sc : nullptr, ref, o, d, which, inside, t, cpos, sk.inside(), src.hpos + path, src.hnrm + path,
                              src.spos ? src.spos + path : nullptr);
     }
     if (same) return false;
@@ -732,7 +767,7 @@ constexpr int kStreamThreads = 256;
 #define RTC_TRACE_THREADS 128
 #endif
 #ifndef RTC_TRACE_MIN_BLOCKS
-#define RTC_TRACE_MIN_BLOCKS 7
+#define RTC_TRACE_MIN_BLOCKS 8
 #endif
 #ifndef RTC_Q8_PRMT
 #define RTC_Q8_PRMT 0
@@ -741,7 +776,7 @@ constexpr int kStreamThreads = 256;
 #define RTC_PREFETCH 0
 #endif
 #ifndef RTC_Q8_SMEM_STATE
-#define RTC_Q8_SMEM_STATE 1
+#define RTC_Q8_SMEM_STATE 2
 #endif
 #ifndef RTC_Q8_PACKED
 #define RTC_Q8_PACKED 1
