@@ -40,18 +40,18 @@ __device__ __forceinline__ float rsqrt_(float a) { return sqrtf(a); }
 __device__ __forceinline__ double rsqrt_(double a) { return sqrt(a); }
 __device__ __forceinline__ float rrcp(float a) { return __frcp_rn(a); }
 __device__ __forceinline__ double rrcp(double a) { return 1.0 / a; }
-// Intersection arithmetic of the f32 mode: the hardware approximations (MUFU.RCP / MUFU.SQRT, <= 2 ulp), which have no
-// out-of-line slow path -- an IEEE division or square root compiles to a subroutine call whose calling convention
+// Intersection arithmetic of the f32 mode: the hardware approximations (one MUFU.RCP / MUFU.SQRT, <= 2 ulp, subnormals
+// flushed), which have no out-of-line slow path -- an IEEE division or square root compiles to a subroutine call whose calling convention
 // constrains register allocation around the whole traversal loop. f64 mode keeps the exact operations.
 __device__ __forceinline__ float xrcp(float a) {
   float r;
-  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
   return r;
 }
 __device__ __forceinline__ double xrcp(double a) { return 1.0 / a; }
 __device__ __forceinline__ float xsqrt(float a) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
   return r;
 }
 __device__ __forceinline__ double xsqrt(double a) { return sqrt(a); }
@@ -850,7 +850,7 @@ struct TraceIO {
 // ray, so a plain while-while loop (all lanes reach a leaf before any is tested) leaves ~3/4 of the lanes idle.
 // The per-lane stack holds (node, box near) pairs so stale entries are discarded without fetching the node.
 #ifndef RTC_REFILL
-#define RTC_REFILL 24
+#define RTC_REFILL 26
 #endif
 #ifndef RTC_LEAF_T
 #define RTC_LEAF_T 8
@@ -1120,6 +1120,10 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
   V3<R> o = mk3(0.f, 0.f, 0.f), inv = o;
 #define RTC_O() o
 #define RTC_INV() inv
+#elif RTC_Q8_SMEM_STATE == 3  // the reciprocal direction (node body only) in shared memory, the origin in registers
+  V3<R> o = mk3(0.f, 0.f, 0.f);
+#define RTC_O() o
+#define RTC_INV() mk3(__uint_as_float(RTC_SW(8)), __uint_as_float(RTC_SW(9)), __uint_as_float(RTC_SW(10)))
 #else  // origin and reciprocal direction too: read back at the top of each node / leaf body
 #define RTC_O() mk3(__uint_as_float(RTC_SW(5)), __uint_as_float(RTC_SW(6)), __uint_as_float(RTC_SW(7)))
 #define RTC_INV() mk3(__uint_as_float(RTC_SW(8)), __uint_as_float(RTC_SW(9)), __uint_as_float(RTC_SW(10)))
@@ -1138,10 +1142,14 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
   // hit bits are stored at position slot ^ octinv so that the highest set bit is the child to visit first
   uint32_t igx = 0, igy = 0, lgx = 0, lgy = 0;
 
+  bool lanes_changed = true;  // warp-uniform: some lane finished its ray since the idle lanes were last counted
   for (;;) {
-    const unsigned m_idle = __ballot_sync(0xFFFFFFFFu, !active);
+    unsigned m_idle = 0;
+    if (lanes_changed) m_idle = __ballot_sync(0xFFFFFFFFu, !active);
+    lanes_changed = false;
     if (m_idle == 0xFFFFFFFFu || (!exhausted && __popc(m_idle) > 32 - kRefill)) {
       // ---- refill ------------------------------------------------------------------------------------------
+      lanes_changed = true;  // recount after the refill (and keep coming back here once the queue is exhausted)
       if (finished) {  // (distance, slot | inside | which): position and normal are completed by finalize_hit in k_shade
         R w;
         set_code(w, best.code);
@@ -1167,7 +1175,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
           V4<R> dv = ld4(&io.dir[npath]);
           V4<R> op = ld4(&io.in_hpos[npath]);
           const uint32_t code = code_of(io.in_hnrm[npath].w);
-#if RTC_Q8_SMEM_STATE < 2
+#if RTC_Q8_SMEM_STATE < 2 || RTC_Q8_SMEM_STATE == 3
           o = xyz(op);
 #else
           const V3<R> o = xyz(op);
@@ -1270,10 +1278,10 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         const uint32_t nzw[2] = {nz_ ? w2.z : w1[4], nz_ ? w2.w : w1[5]}, fzw[2] = {nz_ ? w1[4] : w2.z, nz_ ? w1[5] : w2.w};
 #if RTC_Q8_PACKED
         // two children per FFMA2; the hit mask is gathered from the sign bits of (far - near) with one funnel shift per
-        // child, which leaves child c at bit 7 - c = c ^ 7: the octant permutation below absorbs the reversal
+        // child, children taken from slot 7 down so that child c ends at bit c
         uint32_t acc = 0;
 #pragma unroll
-        for (int c = 0; c < 8; c += 2) {
+        for (int c = 6; c >= 0; c -= 2) {
           const int wi = c >> 2, k = c & 3;
           float tnx0, tnx1, tny0, tny1, tnz0, tnz1, tfx0, tfx1, tfy0, tfy1, tfz0, tfz1;
           ffma2(tnx0, tnx1, qbyte(nxw[wi], k), qbyte(nxw[wi], k + 1), ax, bx);
@@ -1289,25 +1297,23 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
           float df0, df1, db0, db1;
           fsub2(df0, df1, fr0, fr1, nr0, nr1);
           fsub2(db0, db1, best.t, best.t, nr0, nr1);
-          acc = __funnelshift_l(__float_as_uint(df0) | __float_as_uint(fr0) | __float_as_uint(db0), acc, 1);
           acc = __funnelshift_l(__float_as_uint(df1) | __float_as_uint(fr1) | __float_as_uint(db1), acc, 1);
+          acc = __funnelshift_l(__float_as_uint(df0) | __float_as_uint(fr0) | __float_as_uint(db0), acc, 1);
 #else
           const float nr0 = fmaxf(fmaxf(fmaxf(tnx0, tny0), tnz0), 0.0f), nr1 = fmaxf(fmaxf(fmaxf(tnx1, tny1), tnz1), 0.0f);
           const float fr0 = fminf(fminf(fminf(tfx0, tfy0), tfz0), best.t), fr1 = fminf(fminf(fminf(tfx1, tfy1), tfz1), best.t);
           float df0, df1;
           fsub2(df0, df1, fr0, fr1, nr0, nr1);  // negative <=> near > far (x - x = +0; no NaN: every term is finite)
-          acc = __funnelshift_l(__float_as_uint(df0), acc, 1);
           acc = __funnelshift_l(__float_as_uint(df1), acc, 1);
+          acc = __funnelshift_l(__float_as_uint(df0), acc, 1);
 #endif
         }
-        const uint32_t hitrev = ~acc & 0xFFu;  // bit 7 - c set <=> child c is hit
-        const uint32_t imrev = __brev(imask) >> 24, lmrev = __brev(lmask) >> 24;
-        uint32_t hb = (hitrev & imrev) | ((hitrev & lmrev) << 8);
-        // reversed slot order -> visit order: bit (s ^ 7) moves to position s ^ octinv, i.e. an xor by (octinv ^ 7)
-        const uint32_t px = octinv ^ 7u;
-        if (px & 4u) hb = ((hb & 0x0F0Fu) << 4) | ((hb >> 4) & 0x0F0Fu);
-        if (px & 2u) hb = ((hb & 0x3333u) << 2) | ((hb >> 2) & 0x3333u);
-        if (px & 1u) hb = ((hb & 0x5555u) << 1) | ((hb >> 1) & 0x5555u);
+        const uint32_t hitbits = ~acc;  // bit c set <=> child c is hit (bits 8.. are garbage, masked below)
+        uint32_t hb = (hitbits & imask) | ((hitbits & lmask) << 8);
+        // slot order -> visit order: bit s moves to position s ^ octinv (three conditional swaps)
+        if (octinv & 4u) hb = ((hb & 0x0F0Fu) << 4) | ((hb >> 4) & 0x0F0Fu);
+        if (octinv & 2u) hb = ((hb & 0x3333u) << 2) | ((hb >> 2) & 0x3333u);
+        if (octinv & 1u) hb = ((hb & 0x5555u) << 1) | ((hb >> 1) & 0x5555u);
 #else
         uint32_t hitbits = 0;
 #pragma unroll
@@ -1349,6 +1355,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         test_leaf<R>(sc, ref_of(pr), pr, R(0), RTC_O(), RTC_D(), sk, src, RTC_PATH(), best);
       }
     }
+    bool done_now = false;
     if (active && (lgy >> 8) == 0 && (igy >> 8) == 0) {
       if (sp > 0) {
         sp--;
@@ -1358,8 +1365,10 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
       } else {
         active = false;
         finished = true;
+        done_now = true;
       }
     }
+    lanes_changed = __any_sync(0xFFFFFFFFu, done_now);
   }
 #undef RTC_O
 #undef RTC_INV
