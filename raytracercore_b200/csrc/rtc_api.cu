@@ -920,7 +920,7 @@ struct Timed {
   }
 };
 
-// One wavefront over `band`: raygen, (trace, shade, compact) x (recursion+1), then accumulate or export.
+// One wavefront over `band`: raygen, (trace, shade + compaction, bookkeeping) x (recursion+1), then accumulate or export.
 template <typename R>
 int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb, bool debug) {
   LaunchCfg cfg{ctx->stream, ctx->sm_count, ctx->counters};
@@ -1522,7 +1522,8 @@ int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t
         CU(cudaMemcpyAsync(&fres, ctx->d_dbg_fresnel, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       else
         CU(cudaMemcpyAsync(&fres32, ctx->d_dbg_fresnel, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaMemcpyAsync(&alive, ctx->d_queue[i & 1], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      // k_shade appended the path to the next bounce's queue iff it is still alive
+      CU(cudaMemcpyAsync(&alive, &ctx->d_ctl->count[(i & 1) ^ 1], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
       if (sizeof(R) == 4) fres = (double)fres32;
       return RTC_OK;
@@ -1537,7 +1538,7 @@ int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t
     out[i].pad = 0;
     out[i].fresnel_ratio = fres;
     *n_out = i + 1;
-    if (alive & Q_DEAD) break;  // the path ended at bounce i
+    if (alive == 0) break;  // the path ended at bounce i
   }
   ctx->par = saved;
   return RTC_OK;

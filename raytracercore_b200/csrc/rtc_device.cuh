@@ -1393,14 +1393,23 @@ __device__ __forceinline__ R luminance(R r, R g, R b) { return (R(0.299) * r + R
 
 // shade: one bounce of Raytracer.GetColor (Raytracing/Raytracer.cs:71-245) for every live path: terminal tests,
 // RandomShine, Fresnel / total internal reflection, lobe roulette, next ray, tint. Terminated paths write their
-// radiance and set Q_DEAD on their queue entry; the others overwrite dir/tint in place.
+// radiance; the survivors overwrite dir/tint in place and are appended to the next bounce's queue by a warp-aggregated
+// stream compaction (ballot + popc + one atomicAdd per warp) -- the loop's `break`/`return` of the reference.
 template <typename R>
 __global__ void __launch_bounds__(kStreamThreads) k_shade(SceneView<R> sc, ParamsView<R> par, Band band, PathView<R> pv, int q,
                                                            int cur, int bounce, int identity_queue) {
   const uint32_t count = pv.ctl->count[q];
-  uint32_t* queue = pv.queue[q];
-  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
-    const uint32_t path = identity_queue ? idx : queue[idx];
+  const uint32_t* queue = q ? pv.queue[1] : pv.queue[0];
+  uint32_t* qout = q ? pv.queue[0] : pv.queue[1];
+  uint32_t* out_count = &pv.ctl->count[q ^ 1];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (count + stride - 1) / stride;  // warp-uniform trip count: every lane takes part in the ballots
+  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t rnd = 0; rnd < rounds; rnd++, idx += stride) {
+    bool alive = false;
+    uint32_t path = 0;
+    if (idx < count) {
+    path = identity_queue ? idx : queue[idx];
     V4<R> hp = ld4(&pv.hpos[cur][path]);
     V4<R> hn = ld4(&pv.hnrm[cur][path]);
     const uint32_t code = code_of(hn.w);
@@ -1553,37 +1562,23 @@ __global__ void __launch_bounds__(kStreamThreads) k_shade(SceneView<R> sc, Param
       pv.dbg_type[path] = dbg;
       pv.dbg_fresnel[path] = dbg_f;
     }
-    if (done) {
+    if (done)
       st4(&pv.radiance[path], out_r, out_g, out_b, R(0));
-      queue[idx] = path | Q_DEAD;
-    } else if (identity_queue) {
-      queue[idx] = path;
+    alive = !done;
     }
-  }
-}
-
-// compact: warp-aggregated stream compaction of the queue (one atomicAdd per warp). Also folds the bookkeeping of
-// the bounce: ray counter, reset of the trace cursor, zeroing of the queue length just consumed.
-static __global__ void __launch_bounds__(kStreamThreads) k_compact(const uint32_t* __restrict__ qin, uint32_t* __restrict__ qout,
-                                                             Control* ctl, int q) {
-  const uint32_t count = ctl->count[q];
-  const int lane = threadIdx.x & 31;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t rounds = (count + stride - 1) / stride;
-  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  for (uint32_t r = 0; r < rounds; r++, idx += stride) {
-    uint32_t e = idx < count ? qin[idx] : Q_DEAD;
-    bool alive = !(e & Q_DEAD);
-    uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
     if (mask) {
+      const int lane = threadIdx.x & 31;
       uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&ctl->count[q ^ 1], (uint32_t)__popc(mask));
+      if (lane == 0) base = atomicAdd(out_count, (uint32_t)__popc(mask));
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (alive) qout[base + __popc(mask & ((1u << lane) - 1))] = e;
+      if (alive) qout[base + __popc(mask & ((1u << lane) - 1u))] = path;
     }
   }
 }
 
+// Bookkeeping between bounces (one thread): ray counter, reset of the trace cursor, zeroing of the queue length just
+// consumed (the compaction itself is fused into k_shade).
 static __global__ void k_end_bounce(Control* ctl, int q) {
   ctl->rays += ctl->count[q];
   ctl->count[q] = 0;
@@ -1808,8 +1803,6 @@ cudaError_t Kernels<R>::shade(const LaunchCfg& cfg, const SceneView<R>& sc, cons
 
 template <typename R>
 cudaError_t Kernels<R>::compact(const LaunchCfg& cfg, const PathView<R>& pv, int q, bool) {
-  int grid = cfg.sm_count * 8;
-  k_compact<<<grid, kStreamThreads, 0, cfg.stream>>>(pv.queue[q], pv.queue[q ^ 1], pv.ctl, q);
   k_end_bounce<<<1, 1, 0, cfg.stream>>>(pv.ctl, q);
   return cudaGetLastError();
 }

@@ -43,7 +43,6 @@ constexpr uint32_t HIT_MISS = 0xFFFFFFFFu;
 constexpr uint32_t HIT_INSIDE = 1u << 30;
 constexpr uint32_t HIT_SECOND = 1u << 29;  // the hit is the second entry of the primitive's Hit[] (a sphere's far hit)
 
-constexpr uint32_t Q_DEAD = 0x80000000u;  // queue entry flag written by shade for terminated paths
 
 constexpr int kTraceStack = 128;
 
