@@ -302,9 +302,12 @@ def main():
             ctx.set_params(par)
             ctx.set_camera(cam)
             ctx.clear_accum()
+            if world == 1:
+                # one call: render + read-back, each band's rows streaming out while the next band renders
+                ctx.render_read(step * spp, spp, out)
+                return
             ctx.render((step * world + rank) * spp, spp)
-            if world > 1:
-                ctx.reduce_accum(0)
+            ctx.reduce_accum(0)
             if rank == 0:
                 ctx.read_accum(out)
             else:
@@ -330,8 +333,9 @@ def main():
             rays2 = float(st2.rays)
         e2e = {"value": rays2 / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": dt / e2e_steps * 1e3,
-               "what": "per step: H2D of the baked scene image from pinned host memory, camera+params structs, render, "
-                       "reduce (N>1), D2H of the SampleSet planes to pinned host memory; wall clock, max over ranks"}
+               "what": "per step: H2D of the baked scene image from pinned host memory (shading half behind the first trace "
+                       "launch), camera+params structs, render, reduce (N>1), D2H of the SampleSet planes to pinned host "
+                       "memory (N=1: rtc_render_read, band read-back overlapped with the next band); wall clock, max over ranks"}
 
     if rank == 0:
         n_prims = sc.n_prims

@@ -217,6 +217,10 @@ int rtc_camera_rays(rtc_ctx* ctx, int64_t n, const int32_t* xy, const uint32_t* 
  * samples first_sample .. first_sample+n_samples-1 of every pixel, accumulated like FullRaytracer.cs:326-339.
  * Asynchronous on the context's stream; rtc_sync / rtc_read_accum / rtc_tonemap_argb wait for it. */
 int rtc_render(rtc_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1, uint32_t first_sample, uint32_t n_samples);
+/* One progressive frame end to end: rtc_render over the whole image followed by rtc_read_accum, with the read-back of
+ * each band of rows overlapped with the rendering of the next band (the drain of FullRaytracer.cs:326-344 running
+ * beside the workers). Host buffers are best pinned; any of them may be NULL. Blocks until they are filled. */
+int rtc_render_read(rtc_ctx* ctx, uint32_t first_sample, uint32_t n_samples, double* rgb_sum, uint32_t* samples, uint32_t* misses);
 int rtc_sync(rtc_ctx* ctx);
 
 /* ---- SampleSet[,] (SampleSet.cs:7-44): row-major y*width+x ------------------------------------------ */

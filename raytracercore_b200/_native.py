@@ -101,6 +101,7 @@ SIGNATURES = {
     "rtc_sync": (C.c_int, [_P]),
     "rtc_clear_accum": (C.c_int, [_P]),
     "rtc_read_accum": (C.c_int, [_P, _P, _P, _P]),
+    "rtc_render_read": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _P]),
     "rtc_write_accum": (C.c_int, [_P, _P, _P, _P]),
     "rtc_accum_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "rtc_tonemap_argb": (C.c_int, [_P, C.c_double, C.POINTER(C.c_double), C.c_double, _P]),

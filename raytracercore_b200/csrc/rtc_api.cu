@@ -157,7 +157,15 @@ struct rtc_ctx {
 
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+
+  // copy engine choreography: the shading half of a pinned scene image (materials, ids) is copied on a second stream
+  // behind the geometry half, so traversal starts while it is still in flight; rtc_render_read streams the finished
+  // rows of the accumulation planes back while the next band renders.
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_geom = nullptr, ev_shading = nullptr, ev_band = nullptr;
+  bool shading_pending = false;  // kernels that read materials / ids must first wait for ev_shading
 };
+
 
 namespace {
 
@@ -171,6 +179,23 @@ int fail(rtc_ctx* c, int code, const std::string& msg) {
     if (e__ != cudaSuccess)                                                                              \
       return fail(ctx, RTC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
   } while (0)
+
+int ensure_copy_stream(rtc_ctx* ctx) {
+  if (ctx->copy_stream) return RTC_OK;
+  CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&ctx->ev_geom, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->ev_shading, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->ev_band, cudaEventDisableTiming));
+  return RTC_OK;
+}
+
+// Called before the first launch that reads materials, primitive ids or face normals after an upload.
+int wait_shading_upload(rtc_ctx* ctx) {
+  if (!ctx->shading_pending) return RTC_OK;
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_shading, 0));
+  ctx->shading_pending = false;
+  return RTC_OK;
+}
 
 size_t rsize(const rtc_ctx* c) { return c->precision == RTC_F64 ? sizeof(double) : sizeof(float); }
 
@@ -336,23 +361,49 @@ R round_up(double x) {
   }
 }
 
-// H2D copy of a baked scene image into (reused) device buffers.
+// H2D copy of a baked scene image into (reused) device buffers. A pinned image goes in two halves: what the traversal
+// reads (tree, primitive records, transforms) on the context's stream, then what only shading and export read
+// (materials, ids, face-normal z) on the copy stream, so that ray generation and the first trace launch overlap it.
 int upload_baked_image(rtc_ctx* ctx, const rtc_baked* bk) {
   void** dst[rtc_baked::S_COUNT] = {&ctx->d_nodes, &ctx->d_qnodes, (void**)&ctx->d_unbounded, &ctx->d_prims, &ctx->d_mats,
                                     &ctx->d_xforms, (void**)&ctx->d_aux, (void**)&ctx->d_prim_id, (void**)&ctx->d_id_to_slot,
                                     &ctx->d_prim_nz};
+  const bool shading_seg[rtc_baked::S_COUNT] = {false, false, false, false, true, false, false, true, true, true};
+  const bool split = bk->pinned;
+  if (split) {
+    int rc = ensure_copy_stream(ctx);
+    if (rc) return rc;
+  }
+  if (ctx->shading_pending) {  // an earlier image's shading half is still owed to the main stream: order behind it
+    int rc = wait_shading_upload(ctx);
+    if (rc) return rc;
+  }
   for (int i = 0; i < rtc_baked::S_COUNT; i++) {
     const size_t need = std::max<size_t>(bk->bytes[i], 16);
     if (ctx->seg_cap[i] < need || !*dst[i]) {
       if (*dst[i]) {
         CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
         cudaFree(*dst[i]);
         *dst[i] = nullptr;
       }
       CU(cudaMalloc(dst[i], need));
       ctx->seg_cap[i] = need;
     }
-    if (bk->bytes[i]) CU(cudaMemcpyAsync(*dst[i], bk->host + bk->off[i], bk->bytes[i], cudaMemcpyHostToDevice, ctx->stream));
+  }
+  for (int i = 0; i < rtc_baked::S_COUNT; i++)
+    if (bk->bytes[i] && !(split && shading_seg[i]))
+      CU(cudaMemcpyAsync(*dst[i], bk->host + bk->off[i], bk->bytes[i], cudaMemcpyHostToDevice, ctx->stream));
+  if (split) {
+    // the shading half starts when the geometry half is through (same PCIe link: side by side they would only slow
+    // each other down) and, through the same event, after every earlier kernel that still reads the old materials
+    CU(cudaEventRecord(ctx->ev_geom, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_geom, 0));
+    for (int i = 0; i < rtc_baked::S_COUNT; i++)
+      if (bk->bytes[i] && shading_seg[i])
+        CU(cudaMemcpyAsync(*dst[i], bk->host + bk->off[i], bk->bytes[i], cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_shading, ctx->copy_stream));
+    ctx->shading_pending = true;
   }
   if (bk->bytes[rtc_baked::S_QNODES] == 0 && bk->precision == RTC_F32) {
     // no bounded primitive: the kernel keys on a null qnodes pointer
@@ -946,6 +997,10 @@ int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb,
       Timed t(ctx, RTC_K_TRACE);
       CU(Kernels<R>::trace(cfg, sv, pv, q, prev, cur, ident));
     }
+    if (i == 0) {
+      int rcw = wait_shading_upload(ctx);  // materials may still be arriving behind the first trace launch
+      if (rcw) return rcw;
+    }
     {
       Timed t(ctx, RTC_K_SHADE);
       CU(Kernels<R>::shade(cfg, sv, par, band, pv, q, cur, i, ident));
@@ -964,9 +1019,16 @@ int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb,
   return RTC_OK;
 }
 
+// Host destinations of rtc_render_read: the rows of a band are copied back on the copy stream as soon as the band's
+// last accumulate launch is through, while the next band renders.
+struct ReadBack {
+  double* rgb;
+  uint32_t *samples, *misses;
+};
+
 template <typename R>
 int render_rect(rtc_ctx* ctx, int x0, int y0, int x1, int y1, uint32_t first_sample, uint32_t n_samples, bool accumulate,
-                double* d_out_rgb) {
+                double* d_out_rgb, const ReadBack* rb = nullptr) {
   const int64_t rw = x1 - x0;
   const int64_t cap = std::max<int64_t>(ctx->max_paths, rw);
   int rc = ensure_pool(ctx, cap);
@@ -985,6 +1047,14 @@ int render_rect(rtc_ctx* ctx, int x0, int y0, int x1, int y1, uint32_t first_sam
       b.n_paths = (uint32_t)(npix * b.n_samples);
       rc = run_band<R>(ctx, b, accumulate, d_out_rgb, false);
       if (rc) return rc;
+    }
+    if (rb) {  // full-width bands: rows [ya, yb) are contiguous in the row-major planes
+      const size_t off = (size_t)ya * ctx->acc_w, cnt = (size_t)(yb - ya) * ctx->acc_w;
+      CU(cudaEventRecord(ctx->ev_band, ctx->stream));
+      CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band, 0));
+      if (rb->rgb) CU(cudaMemcpyAsync(rb->rgb + off * 3, ctx->d_rgb + off * 3, cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+      if (rb->samples) CU(cudaMemcpyAsync(rb->samples + off, ctx->d_samples + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+      if (rb->misses) CU(cudaMemcpyAsync(rb->misses + off, ctx->d_misses + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
   }
   return RTC_OK;
@@ -1121,6 +1191,13 @@ void rtc_destroy(rtc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->ev_geom);
+    cudaEventDestroy(ctx->ev_shading);
+    cudaEventDestroy(ctx->ev_band);
+  }
   rtc_comm_destroy(ctx);
   drain_timing(ctx);
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
@@ -1331,6 +1408,8 @@ int rtc_trace_closest(rtc_ctx* ctx, int64_t n, const rtc_ray* rays, const rtc_hi
   if (rc) return rc;
   if (n == 0) return RTC_OK;
   cudaSetDevice(ctx->device);
+  rc = wait_shading_upload(ctx);
+  if (rc) return rc;
   return ctx->precision == RTC_F64 ? trace_batch<double>(ctx, n, rays, skip, out) : trace_batch<float>(ctx, n, rays, skip, out);
 }
 
@@ -1377,10 +1456,36 @@ int rtc_render(rtc_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1, uin
                                    : render_rect<float>(ctx, x0, y0, x1, y1, first_sample, n_samples, true, nullptr);
 }
 
+int rtc_render_read(rtc_ctx* ctx, uint32_t first_sample, uint32_t n_samples, double* rgb_sum, uint32_t* samples, uint32_t* misses) {
+  if (!ctx) return RTC_ERR_INVALID;
+  int rc = ready(ctx, true);
+  if (rc) return rc;
+  cudaSetDevice(ctx->device);
+  rc = ensure_accum(ctx);
+  if (rc) return rc;
+  rc = ensure_copy_stream(ctx);
+  if (rc) return rc;
+  ReadBack rb{rgb_sum, samples, misses};
+  const int w = ctx->par.width, h = ctx->par.height;
+  if (n_samples == 0) {  // nothing to render: a plain read of the whole planes
+    return rtc_read_accum(ctx, rgb_sum, samples, misses);
+  }
+  rc = ctx->precision == RTC_F64 ? render_rect<double>(ctx, 0, 0, w, h, first_sample, n_samples, true, nullptr, &rb)
+                                 : render_rect<float>(ctx, 0, 0, w, h, first_sample, n_samples, true, nullptr, &rb);
+  // both streams are drained even on error: the caller owns the host buffers again when this returns
+  cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream);
+  drain_timing(ctx);
+  if (rc) return rc;
+  CU(e1);
+  CU(e2);
+  return RTC_OK;
+}
+
 int rtc_sync(rtc_ctx* ctx) {
   if (!ctx) return RTC_ERR_INVALID;
   cudaSetDevice(ctx->device);
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
   drain_timing(ctx);
   return RTC_OK;
 }
@@ -1476,6 +1581,8 @@ int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t
   if (rc) return rc;
   if (x < 0 || y < 0 || x >= ctx->par.width || y >= ctx->par.height) return fail(ctx, RTC_ERR_INVALID, "pixel outside the image");
   cudaSetDevice(ctx->device);
+  rc = wait_shading_upload(ctx);
+  if (rc) return rc;
   rc = ensure_pool(ctx, ctx->max_paths);
   if (rc) return rc;
   if (!ctx->d_dbg_type) {
@@ -1551,6 +1658,8 @@ int rtc_debug_raycast(rtc_ctx* ctx, int32_t mode, int32_t* out) {
   int rc = ready(ctx, true);
   if (rc) return rc;
   cudaSetDevice(ctx->device);
+  rc = wait_shading_upload(ctx);
+  if (rc) return rc;
   const int w = ctx->par.width, h = ctx->par.height;
   const size_t n = (size_t)w * h;
   int32_t* d_out = nullptr;

@@ -140,6 +140,19 @@ class Context:
         x0, y0, x1, y1 = rect if rect is not None else (0, 0, self.width, self.height)
         self._ck(N.lib.rtc_render(self._h, x0, y0, x1, y1, first_sample, n_samples))
 
+    def render_read(self, first_sample, n_samples, out=None):
+        """rtc_render over the whole image + rtc_read_accum, band read-back overlapped with rendering.
+        out: optional (rgb f64 [h,w,3], samples u32 [h,w], misses u32 [h,w]) arrays or raw pointers (e.g. pinned)."""
+        if out is None:
+            rgb = np.empty((self.height, self.width, 3), np.float64)
+            s = np.empty((self.height, self.width), np.uint32)
+            m = np.empty((self.height, self.width), np.uint32)
+            self._ck(N.lib.rtc_render_read(self._h, first_sample, n_samples, _ptr(rgb), _ptr(s), _ptr(m)))
+            return rgb, s, m
+        ptrs = [(_ptr(a) if isinstance(a, np.ndarray) else a) for a in out]
+        self._ck(N.lib.rtc_render_read(self._h, first_sample, n_samples, *ptrs))
+        return out
+
     def sync(self):
         self._ck(N.lib.rtc_sync(self._h))
 
