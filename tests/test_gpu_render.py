@@ -10,7 +10,7 @@ import pytest
 
 import oracle as O
 from conftest import SCENES
-from raytracercore_b200 import RTC_OPT_COUNTERS, RTC_F32, RTC_F64, Context, FullRaytracer, Scene
+from raytracercore_b200 import RAY_DT, RTC_OPT_COUNTERS, RTC_F32, RTC_F64, Context, FullRaytracer, Scene
 from raytracercore_b200 import _native as N
 
 pytestmark = pytest.mark.gpu
@@ -281,6 +281,47 @@ def test_full_size_properties_1m_triangle_scene():
     ctx.render(0, 2)
     rgb3, s3, m3 = ctx.read_accum()
     assert np.array_equal(rgb2, rgb3) and np.array_equal(s2, s3) and np.array_equal(m2, m3)  # idempotent + additive
+    ctx.close()
+
+
+def test_odd_image_sizes_empty_scene_and_non_finite_rays():
+    """Ragged sizes (1x1, a width that is no multiple of the warp, more bands than rows), the no-primitive scene
+    (rejected with an error text, like the reference's missing accelerator assertion, Scene.cs:116) and rays with
+    non-finite components (f32 mode: reported as misses, never traversed)."""
+    for w, h in ((1, 1), (37, 5), (5, 67)):
+        sc = cornell(w, h, 4)
+        ora = O.OracleScene(sc, seed=9)
+        ctx = Context(0, RTC_F64)
+        ctx.set_option(N.RTC_OPT_MAX_PATHS, 1024)
+        ctx.load(sc, seed=9)
+        img = ctx.render_samples(2)
+        ref = ora.render_samples(2)
+        assert img.shape == (h, w, 3)
+        assert np.isclose(img, ref, rtol=1e-9, atol=1e-12).all(axis=2).mean() >= (0.99 if w * h > 100 else 1.0)
+        ctx.render(0, 3)
+        rgb, s, m = ctx.read_accum()
+        assert np.all(s + m == 3)
+        got = ctx.render_read(3, 2)
+        assert np.all(got[1] + got[2] == 5)
+        ctx.close()
+    empty = Scene.from_string("size 8 8\ncamera 0 0 -5 0 0 0 0 1 0 40\n")
+    ctx = Context(0, RTC_F32)
+    ctx.upload_scene(empty)
+    with pytest.raises(N.RtcError) as e:
+        ctx.build_bvh()
+    assert e.value.code == N.RTC_ERR_INVALID and "no primitives" in str(e.value)
+    ctx.close()
+    sc = cornell(8, 8, 4)
+    ctx = Context(0, RTC_F32)
+    ctx.load(sc, seed=1)
+    r = np.zeros(6, RAY_DT)
+    r["origin"] = [[0, 0, -1]] * 6
+    r["dir"] = [[0, 0, 1], [np.nan, 0, 1], [0, np.inf, 0], [0, 0, 1], [0, 0, 1], [0, 0, 1]]
+    r["origin"][3] = [np.nan, 0, 0]
+    r["origin"][4] = [0, -np.inf, 0]
+    h = ctx.trace_closest(r)
+    assert h["prim"][0] >= 0 and h["prim"][5] == h["prim"][0]
+    assert np.all(h["prim"][1:5] == -1)
     ctx.close()
 
 
