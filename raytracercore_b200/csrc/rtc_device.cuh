@@ -769,20 +769,8 @@ constexpr int kStreamThreads = 256;
 #ifndef RTC_TRACE_MIN_BLOCKS
 #define RTC_TRACE_MIN_BLOCKS 8
 #endif
-#ifndef RTC_Q8_PRMT
-#define RTC_Q8_PRMT 0
-#endif
 #ifndef RTC_PREFETCH
 #define RTC_PREFETCH 0
-#endif
-#ifndef RTC_Q8_SMEM_STATE
-#define RTC_Q8_SMEM_STATE 2
-#endif
-#ifndef RTC_Q8_PACKED
-#define RTC_Q8_PACKED 1
-#endif
-#ifndef RTC_Q8_SIGNFOLD
-#define RTC_Q8_SIGNFOLD 0
 #endif
 constexpr int kTraceThreads = RTC_TRACE_THREADS;
 constexpr int kTraceMinBlocks = RTC_TRACE_MIN_BLOCKS;
@@ -1046,32 +1034,26 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
 // ---------------------------------------------------------------------------------------------------------
 // trace, f32 production mode: the same warp-synchronous scheduler over the quantised 8-wide tree (CNode).
 //   node step: pop the highest-priority pending child of the current inner group, fetch its node with
-//              2 x LDG.256 + 1 x LDG.128, decode the 8 child boxes (one PRMT + one FFMA per bound: byte q becomes the
-//              float 2^23 + q, the 2^23 is folded into the FMA addend) and intersect them; the hits form one inner group
-//              and one leaf group, addressed implicitly (base + popcount), so at most ONE stack entry is pushed;
+//              2 x LDG.256 + 1 x LDG.128, decode the 8 child boxes (one IDP.4A per bound: byte q becomes the float
+//              2^23 + q, the 2^23 is folded into the FMA addend; one FFMA2 per bound PAIR) and intersect them; the hits
+//              form one inner group and one leaf group, addressed implicitly (base + popcount), so at most ONE stack
+//              entry is pushed;
 //   leaf step: pop the highest-priority pending leaf of the leaf group and test its primitive.
-// The stack lives in shared memory as [entry][thread] (conflict-free for any per-lane depth).
+// Register budget (64 -> 8 CTAs = 32 warps per SM, measured optimum): everything a lane needs only now and then lives in
+// shared memory, one 4-byte column per thread and field -- the stack [entry][thread] (conflict-free for any per-lane
+// depth), then direction, path id, skip code, origin and reciprocal direction -- and is addressed from ONE per-thread
+// shared-window byte address (`sm`); the kernel contains no call (see xrcp/xsqrt) and no conditionally defined values
+// that would stay live around the loop (see sphere_hits).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ldg256(const void* p, uint32_t (&w)[8]) {
   asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                : "l"(p));
 }
-__device__ __forceinline__ float qbyte(uint32_t w, int k) {  // float(2^23 + byte k of w)
-#if RTC_Q8_PRMT
-  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)k));
-#else
-  // dp4a(w, 1 << 8k, 2^23 as float bits) = byte k + 0x4B000000: one IDP.4A on the FMA-heavy pipe instead of a PRMT on the
-  // (half-rate, saturated) ALU pipe
-  return __uint_as_float(__dp4a(w, 1u << (8 * k), 0x4B000000u));
-#endif
-}
+// float(2^23 + byte k of w): dp4a(w, 1 << 8k, 2^23 as float bits) = one IDP.4A on the FMA-heavy pipe instead of a PRMT on
+// the (half-rate, busier) ALU pipe
+__device__ __forceinline__ float qbyte(uint32_t w, int k) { return __uint_as_float(__dp4a(w, 1u << (8 * k), 0x4B000000u)); }
 
-#ifdef RTC_TRACE_MAXNREG  // tuning: an explicit register budget instead of one derived from the resident-CTA target
-#define RTC_Q8_BOUNDS __maxnreg__(RTC_TRACE_MAXNREG)
-#else
-#define RTC_Q8_BOUNDS __launch_bounds__(kTraceThreads, kTraceMinBlocks)
-#endif
 // Packed f32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two children's slab distances.
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
   unsigned long long A, B, C, D;
@@ -1088,46 +1070,45 @@ __device__ __forceinline__ void fsub2(float& d0, float& d1, float a0, float a1, 
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
 }
+// shared-window accesses through a 32-bit byte address (no generic pointer, no base recomputation per access)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y));
+}
+
+#ifdef RTC_TRACE_MAXNREG  // tuning: an explicit register budget instead of one derived from the resident-CTA target
+#define RTC_Q8_BOUNDS __maxnreg__(RTC_TRACE_MAXNREG)
+#else
+#define RTC_Q8_BOUNDS __launch_bounds__(kTraceThreads, kTraceMinBlocks)
+#endif
+constexpr int kQ8StateWords = 11;  // per-thread cold state after the stack: d.xyz, path, skip code, o.xyz, inv.xyz
 
 template <bool COUNT>
 __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io) {
   using R = float;
-  extern __shared__ uint2 s_stack[];  // [sc.q_stack][kTraceThreads], then the per-lane cold state (RTC_Q8_SMEM_STATE)
-#if RTC_Q8_SMEM_STATE
-  // Ray state that only the leaf and refill bodies read (direction, path id, skip code) lives in shared memory: five
-  // registers fewer across the node step, which is what bounds the number of resident warps.
-  // (indexed off the extern array every time: 32-bit shared-window addresses, no generic pointers held in registers)
-#define RTC_SW(k) (reinterpret_cast<uint32_t*>(s_stack)[(2 * sc.q_stack + (k)) * kTraceThreads + threadIdx.x])
-#define RTC_D() mk3(__uint_as_float(RTC_SW(0)), __uint_as_float(RTC_SW(1)), __uint_as_float(RTC_SW(2)))
-#define RTC_PATH() RTC_SW(3)
-#define RTC_SKIP() RTC_SW(4)
-#else
-#define RTC_D() d
-#define RTC_PATH() path
-#define RTC_SKIP() sk.code
-#endif
+  extern __shared__ uint2 s_stack[];  // [sc.q_stack][kTraceThreads] stack entries, then kQ8StateWords x [kTraceThreads] words
+  constexpr uint32_t kStackStride = kTraceThreads * 8u, kCol = kTraceThreads * 4u;
+  // this thread's stack column; its state columns start at sm + state_off
+  const uint32_t sm = (uint32_t)__cvta_generic_to_shared(s_stack) + threadIdx.x * 8u;
+  const uint32_t st = sm + (uint32_t)sc.q_stack * kStackStride - threadIdx.x * 4u;  // byte address of state word 0
+  enum { S_DX = 0, S_DY, S_DZ, S_PATH, S_SKIP, S_OX, S_OY, S_OZ, S_IX, S_IY, S_IZ };
   const uint32_t count = *io.count;
-#define RTC_LANE() ((int)(threadIdx.x & 31))
   uint32_t n_nodes = 0, n_prims = 0, n_node_steps = 0, n_leaf_steps = 0;
-  bool active = false, finished = false, exhausted = false;
-#if !RTC_Q8_SMEM_STATE
-  uint32_t path = 0;
-  V3<R> d = mk3(0.f, 0.f, 0.f);
-  Skip<R> sk;
-  sk.code = HIT_MISS;
-#endif
-#if RTC_Q8_SMEM_STATE < 2
-  V3<R> o = mk3(0.f, 0.f, 0.f), inv = o;
-#define RTC_O() o
-#define RTC_INV() inv
-#elif RTC_Q8_SMEM_STATE == 3  // the reciprocal direction (node body only) in shared memory, the origin in registers
-  V3<R> o = mk3(0.f, 0.f, 0.f);
-#define RTC_O() o
-#define RTC_INV() mk3(__uint_as_float(RTC_SW(8)), __uint_as_float(RTC_SW(9)), __uint_as_float(RTC_SW(10)))
-#else  // origin and reciprocal direction too: read back at the top of each node / leaf body
-#define RTC_O() mk3(__uint_as_float(RTC_SW(5)), __uint_as_float(RTC_SW(6)), __uint_as_float(RTC_SW(7)))
-#define RTC_INV() mk3(__uint_as_float(RTC_SW(8)), __uint_as_float(RTC_SW(9)), __uint_as_float(RTC_SW(10)))
-#endif
+  // lane state in `sp`: >= 0 traversing (= stack depth), kFinished = result not written yet, kEmpty = no ray
+  constexpr int kFinished = -1, kEmpty = -2;
+  int sp = kEmpty;
+  uint32_t exhausted = 0;      // warp-uniform: the queue has no more entries
+  uint32_t lanes_changed = 1;  // warp-uniform: some lane finished its ray since the idle lanes were last counted
   uint32_t octinv = 0;
   SkipSrc<R> src;
   src.hpos = io.in_hpos;
@@ -1137,74 +1118,58 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
   best.t = Num<R>::inf();
   best.near_ = 0;
   best.code = HIT_MISS;
-  int sp = 0;
   // current groups: inner (igx = child_base, igy = hits << 8 | imask) and leaf (lgx = prim_base, lgy = hits << 8 | lmask);
   // hit bits are stored at position slot ^ octinv so that the highest set bit is the child to visit first
   uint32_t igx = 0, igy = 0, lgx = 0, lgy = 0;
 
-  bool lanes_changed = true;  // warp-uniform: some lane finished its ray since the idle lanes were last counted
   for (;;) {
     unsigned m_idle = 0;
-    if (lanes_changed) m_idle = __ballot_sync(0xFFFFFFFFu, !active);
-    lanes_changed = false;
+    if (lanes_changed) m_idle = __ballot_sync(0xFFFFFFFFu, sp < 0);
+    lanes_changed = 0;
     if (m_idle == 0xFFFFFFFFu || (!exhausted && __popc(m_idle) > 32 - kRefill)) {
       // ---- refill ------------------------------------------------------------------------------------------
-      lanes_changed = true;  // recount after the refill (and keep coming back here once the queue is exhausted)
-      if (finished) {  // (distance, slot | inside | which): position and normal are completed by finalize_hit in k_shade
+      lanes_changed = 1;  // recount after the refill (and keep coming back here once the queue is exhausted)
+      if (sp == kFinished) {  // (distance, slot | inside | which): position and normal are completed by finalize_hit in k_shade
         R w;
         set_code(w, best.code);
-        const uint32_t fpath = RTC_PATH();
+        const uint32_t fpath = lds32(st + S_PATH * kCol);
         st4(&io.out_hpos[fpath], R(0), R(0), R(0), best.t);
         st4(&io.out_hnrm[fpath], R(0), R(0), R(0), w);
-        finished = false;
+        sp = kEmpty;
       }
       if (exhausted) {
         if (m_idle == 0xFFFFFFFFu) break;
         continue;
       }
+      const int lane = threadIdx.x & 31;
       uint32_t base = 0;
       const int leader = __ffs(m_idle) - 1;
-      if (RTC_LANE() == leader) base = atomicAdd(&io.ctl->work_trace, (uint32_t)__popc(m_idle));
+      if (lane == leader) base = atomicAdd(&io.ctl->work_trace, (uint32_t)__popc(m_idle));
       base = __shfl_sync(0xFFFFFFFFu, base, leader);
       bool got = true;
-      if (!active) {
-        const uint32_t idx = base + __popc(m_idle & ((1u << RTC_LANE()) - 1u));
+      if (sp < 0) {
+        const uint32_t idx = base + __popc(m_idle & ((1u << lane) - 1u));
         got = idx < count;
         if (got) {
           const uint32_t npath = io.queue ? io.queue[idx] : idx;
           V4<R> dv = ld4(&io.dir[npath]);
           V4<R> op = ld4(&io.in_hpos[npath]);
           const uint32_t code = code_of(io.in_hnrm[npath].w);
-#if RTC_Q8_SMEM_STATE < 2 || RTC_Q8_SMEM_STATE == 3
-          o = xyz(op);
-#else
-          const V3<R> o = xyz(op);
-          RTC_SW(5) = __float_as_uint(o.x);
-          RTC_SW(6) = __float_as_uint(o.y);
-          RTC_SW(7) = __float_as_uint(o.z);
-#endif
-#if RTC_Q8_SMEM_STATE
-          const V3<R> d = xyz(dv);
-          RTC_SW(0) = __float_as_uint(d.x);
-          RTC_SW(1) = __float_as_uint(d.y);
-          RTC_SW(2) = __float_as_uint(d.z);
-          RTC_PATH() = npath;
-          RTC_SKIP() = code;
+          const V3<R> o = xyz(op), d = xyz(dv);
+          const V3<R> inv = mk3(clamped_rcp(d.x), clamped_rcp(d.y), clamped_rcp(d.z));
+          sts32(st + S_DX * kCol, __float_as_uint(d.x));
+          sts32(st + S_DY * kCol, __float_as_uint(d.y));
+          sts32(st + S_DZ * kCol, __float_as_uint(d.z));
+          sts32(st + S_PATH * kCol, npath);
+          sts32(st + S_SKIP * kCol, code);
+          sts32(st + S_OX * kCol, __float_as_uint(o.x));
+          sts32(st + S_OY * kCol, __float_as_uint(o.y));
+          sts32(st + S_OZ * kCol, __float_as_uint(o.z));
+          sts32(st + S_IX * kCol, __float_as_uint(inv.x));
+          sts32(st + S_IY * kCol, __float_as_uint(inv.y));
+          sts32(st + S_IZ * kCol, __float_as_uint(inv.z));
           Skip<R> sk;
           sk.code = code;
-#else
-          d = xyz(dv);
-          path = npath;
-          sk.code = code;
-#endif
-#if RTC_Q8_SMEM_STATE < 2
-          inv = mk3(clamped_rcp(d.x), clamped_rcp(d.y), clamped_rcp(d.z));
-#else
-          const V3<R> inv = mk3(clamped_rcp(d.x), clamped_rcp(d.y), clamped_rcp(d.z));
-          RTC_SW(8) = __float_as_uint(inv.x);
-          RTC_SW(9) = __float_as_uint(inv.y);
-          RTC_SW(10) = __float_as_uint(inv.z);
-#endif
           const uint32_t oct = (rsignbit(d.x) ? 1u : 0u) | (rsignbit(d.y) ? 2u : 0u) | (rsignbit(d.z) ? 4u : 0u);
           octinv = 7u ^ oct;
           best.t = Num<R>::inf();
@@ -1225,15 +1190,14 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
           igy = (sc.qnodes && finite) ? (((1u << (0u ^ octinv)) << 8) | 1u) : 0u;
           lgx = 0;
           lgy = 0;
-          active = true;
         }
       }
-      exhausted = !__all_sync(0xFFFFFFFFu, got);
+      exhausted = __all_sync(0xFFFFFFFFu, got) ? 0u : 1u;
       continue;
     }
 
-    const bool want_leaf = active && (lgy >> 8) != 0;
-    const bool want_node = active && !want_leaf && (igy >> 8) != 0;
+    const bool want_leaf = sp >= 0 && (lgy >> 8) != 0;
+    const bool want_node = sp >= 0 && !want_leaf && (igy >> 8) != 0;
     const unsigned m_leaf = __ballot_sync(0xFFFFFFFFu, want_leaf);
     const unsigned m_node = __ballot_sync(0xFFFFFFFFu, want_node);
 #if RTC_LEAF_T > 0
@@ -1242,7 +1206,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
     if (__popc(m_node) >= __popc(m_leaf) && m_node) {
 #endif
       // ---- node step ---------------------------------------------------------------------------------------
-      if (COUNT && RTC_LANE() == 0) n_node_steps++;
+      if (COUNT && (threadIdx.x & 31) == 0) n_node_steps++;
       if (want_node) {
         const uint32_t hits = igy >> 8;
         const uint32_t b = 31u - (uint32_t)__clz((int)hits);
@@ -1251,7 +1215,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         const uint32_t node = igx + (uint32_t)__popc(imask_g & ((1u << s) - 1u));
         igy &= ~(0x100u << b);
         if ((igy >> 8) != 0) {  // siblings still pending: the group goes to the stack
-          s_stack[sp * kTraceThreads + threadIdx.x] = make_uint2(igx, igy);
+          sts64(sm + (uint32_t)sp * kStackStride, igx, igy);
           sp++;
         }
         const CNode* np = sc.qnodes + node;
@@ -1266,7 +1230,10 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         const uint32_t imask = em >> 24, lmask = w0[6] & 0xFFu;
         // t = (p + q * step - o) * inv = q * (step * inv) + (p - o) * inv ; q enters as 2^23 + q, so the addend carries
         // -2^23 * step * inv (its rounding is half a grid step: the builder pads every box by one step)
-        const V3<R> ro = RTC_O(), ri = RTC_INV();
+        const V3<R> ro = mk3(__uint_as_float(lds32(st + S_OX * kCol)), __uint_as_float(lds32(st + S_OY * kCol)),
+                             __uint_as_float(lds32(st + S_OZ * kCol)));
+        const V3<R> ri = mk3(__uint_as_float(lds32(st + S_IX * kCol)), __uint_as_float(lds32(st + S_IY * kCol)),
+                             __uint_as_float(lds32(st + S_IZ * kCol)));
         const float ax = sx * ri.x, ay = sy * ri.y, az = sz * ri.z;
         const float bx = fmaf(-8388608.0f, ax, (__uint_as_float(w0[0]) - ro.x) * ri.x);
         const float by = fmaf(-8388608.0f, ay, (__uint_as_float(w0[1]) - ro.y) * ri.y);
@@ -1276,7 +1243,6 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         const uint32_t nxw[2] = {nx_ ? w1[6] : w1[0], nx_ ? w1[7] : w1[1]}, fxw[2] = {nx_ ? w1[0] : w1[6], nx_ ? w1[1] : w1[7]};
         const uint32_t nyw[2] = {ny_ ? w2.x : w1[2], ny_ ? w2.y : w1[3]}, fyw[2] = {ny_ ? w1[2] : w2.x, ny_ ? w1[3] : w2.y};
         const uint32_t nzw[2] = {nz_ ? w2.z : w1[4], nz_ ? w2.w : w1[5]}, fzw[2] = {nz_ ? w1[4] : w2.z, nz_ ? w1[5] : w2.w};
-#if RTC_Q8_PACKED
         // two children per FFMA2; the hit mask is gathered from the sign bits of (far - near) with one funnel shift per
         // child, children taken from slot 7 down so that child c ends at bit c
         uint32_t acc = 0;
@@ -1290,23 +1256,12 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
           ffma2(tfx0, tfx1, qbyte(fxw[wi], k), qbyte(fxw[wi], k + 1), ax, bx);
           ffma2(tfy0, tfy1, qbyte(fyw[wi], k), qbyte(fyw[wi], k + 1), ay, by);
           ffma2(tfz0, tfz1, qbyte(fzw[wi], k), qbyte(fzw[wi], k + 1), az, bz);
-#if RTC_Q8_SIGNFOLD
-          // max(near, 0) <= min(far, best) <=> none of (far - near), far, (best - near) is negative: one OR of sign bits
-          const float nr0 = fmaxf(fmaxf(tnx0, tny0), tnz0), nr1 = fmaxf(fmaxf(tnx1, tny1), tnz1);
-          const float fr0 = fminf(fminf(tfx0, tfy0), tfz0), fr1 = fminf(fminf(tfx1, tfy1), tfz1);
-          float df0, df1, db0, db1;
-          fsub2(df0, df1, fr0, fr1, nr0, nr1);
-          fsub2(db0, db1, best.t, best.t, nr0, nr1);
-          acc = __funnelshift_l(__float_as_uint(df1) | __float_as_uint(fr1) | __float_as_uint(db1), acc, 1);
-          acc = __funnelshift_l(__float_as_uint(df0) | __float_as_uint(fr0) | __float_as_uint(db0), acc, 1);
-#else
           const float nr0 = fmaxf(fmaxf(fmaxf(tnx0, tny0), tnz0), 0.0f), nr1 = fmaxf(fmaxf(fmaxf(tnx1, tny1), tnz1), 0.0f);
           const float fr0 = fminf(fminf(fminf(tfx0, tfy0), tfz0), best.t), fr1 = fminf(fminf(fminf(tfx1, tfy1), tfz1), best.t);
           float df0, df1;
           fsub2(df0, df1, fr0, fr1, nr0, nr1);  // negative <=> near > far (x - x = +0; no NaN: every term is finite)
           acc = __funnelshift_l(__float_as_uint(df1), acc, 1);
           acc = __funnelshift_l(__float_as_uint(df0), acc, 1);
-#endif
         }
         const uint32_t hitbits = ~acc;  // bit c set <=> child c is hit (bits 8.. are garbage, masked below)
         uint32_t hb = (hitbits & imask) | ((hitbits & lmask) << 8);
@@ -1314,24 +1269,6 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         if (octinv & 4u) hb = ((hb & 0x0F0Fu) << 4) | ((hb >> 4) & 0x0F0Fu);
         if (octinv & 2u) hb = ((hb & 0x3333u) << 2) | ((hb >> 2) & 0x3333u);
         if (octinv & 1u) hb = ((hb & 0x5555u) << 1) | ((hb >> 1) & 0x5555u);
-#else
-        uint32_t hitbits = 0;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-          const int wi = c >> 2, k = c & 3;
-          const float tnx = fmaf(qbyte(nxw[wi], k), ax, bx), tny = fmaf(qbyte(nyw[wi], k), ay, by), tnz = fmaf(qbyte(nzw[wi], k), az, bz);
-          const float tfx = fmaf(qbyte(fxw[wi], k), ax, bx), tfy = fmaf(qbyte(fyw[wi], k), ay, by), tfz = fmaf(qbyte(fzw[wi], k), az, bz);
-          const float nr = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.0f);
-          const float fr = fminf(fminf(fminf(tfx, tfy), tfz), best.t);
-          hitbits |= (nr <= fr) ? (1u << c) : 0u;
-        }
-        // slot order -> visit order: bit s moves to position s ^ octinv (three conditional swaps)
-        uint32_t ih = hitbits & imask, lh = hitbits & lmask;
-        uint32_t hb = ih | (lh << 8);
-        if (octinv & 4u) hb = ((hb & 0x0F0Fu) << 4) | ((hb >> 4) & 0x0F0Fu);
-        if (octinv & 2u) hb = ((hb & 0x3333u) << 2) | ((hb >> 2) & 0x3333u);
-        if (octinv & 1u) hb = ((hb & 0x5555u) << 1) | ((hb >> 1) & 0x5555u);
-#endif
         igx = w0[4];
         igy = ((hb & 0xFFu) << 8) | imask;
         lgx = w0[5];
@@ -1339,7 +1276,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
       }
     } else {
       // ---- leaf step ---------------------------------------------------------------------------------------
-      if (COUNT && RTC_LANE() == 0) n_leaf_steps++;
+      if (COUNT && (threadIdx.x & 31) == 0) n_leaf_steps++;
       if (want_leaf) {
         const uint32_t hits = lgy >> 8;
         const uint32_t b = 31u - (uint32_t)__clz((int)hits);
@@ -1348,43 +1285,37 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         lgy &= ~(0x100u << b);
         if (COUNT) n_prims++;
         const PrimRec<R> pr = load_prim(sc, slot);
-#if RTC_Q8_SMEM_STATE
         Skip<R> sk;
-        sk.code = RTC_SKIP();
-#endif
-        test_leaf<R>(sc, ref_of(pr), pr, R(0), RTC_O(), RTC_D(), sk, src, RTC_PATH(), best);
+        sk.code = lds32(st + S_SKIP * kCol);
+        const V3<R> o = mk3(__uint_as_float(lds32(st + S_OX * kCol)), __uint_as_float(lds32(st + S_OY * kCol)),
+                            __uint_as_float(lds32(st + S_OZ * kCol)));
+        const V3<R> d = mk3(__uint_as_float(lds32(st + S_DX * kCol)), __uint_as_float(lds32(st + S_DY * kCol)),
+                            __uint_as_float(lds32(st + S_DZ * kCol)));
+        test_leaf<R>(sc, ref_of(pr), pr, R(0), o, d, sk, src, lds32(st + S_PATH * kCol), best);
       }
     }
     bool done_now = false;
-    if (active && (lgy >> 8) == 0 && (igy >> 8) == 0) {
+    if (sp >= 0 && ((lgy | igy) >> 8) == 0) {
       if (sp > 0) {
         sp--;
-        const uint2 g = s_stack[sp * kTraceThreads + threadIdx.x];
+        const uint2 g = lds64(sm + (uint32_t)sp * kStackStride);
         igx = g.x;
         igy = g.y;
       } else {
-        active = false;
-        finished = true;
+        sp = kFinished;
         done_now = true;
       }
     }
-    lanes_changed = __any_sync(0xFFFFFFFFu, done_now);
+    lanes_changed = __any_sync(0xFFFFFFFFu, done_now) ? 1u : 0u;
   }
-#undef RTC_O
-#undef RTC_INV
-#undef RTC_SW
-#undef RTC_D
-#undef RTC_PATH
-#undef RTC_SKIP
   if (COUNT) {
     atomicAdd(&io.ctl->nodes_visited, (unsigned long long)n_nodes);
     atomicAdd(&io.ctl->prims_tested, (unsigned long long)n_prims);
-    if (RTC_LANE() == 0) {
+    if ((threadIdx.x & 31) == 0) {
       atomicAdd(&io.ctl->node_steps, (unsigned long long)n_node_steps);
       atomicAdd(&io.ctl->leaf_steps, (unsigned long long)n_leaf_steps);
     }
   }
-#undef RTC_LANE
 }
 
 // DoubleColor.Luminance (DoubleColor.cs:76-81)
@@ -1759,7 +1690,7 @@ cudaError_t Kernels<R>::camera_rays(const LaunchCfg& cfg, const CameraView<R>& c
 template <typename R>
 cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, int prev, int cur,
                               bool identity_queue) {
-  const size_t smem = Num<R>::is_f64 ? 0 : (size_t)sc.q_stack * kTraceThreads * sizeof(uint2) + (RTC_Q8_SMEM_STATE >= 2 ? 11 : RTC_Q8_SMEM_STATE ? 5 : 0) * kTraceThreads * sizeof(float);
+  const size_t smem = Num<R>::is_f64 ? 0 : (size_t)sc.q_stack * kTraceThreads * sizeof(uint2) + kQ8StateWords * kTraceThreads * sizeof(float);
   static thread_local size_t per_sm_smem = ~(size_t)0;  // resident CTAs per SM for the stack size last seen (persistent grid = all of them)
   static thread_local int per_sm = 1;
   if (smem != per_sm_smem) {
