@@ -191,6 +191,12 @@ int rtc_upload_bvh(rtc_ctx* ctx, int32_t n_nodes, const rtc_bvh_node* nodes, int
 /* Replacement for BVH.Construct (BVH.cs:50-236): binned-SAH build over the uploaded primitives, leaf boxes
  * exactly as AABB.CreateFromBounded (AABB.cs:20-36); planes are chained above the root. */
 int rtc_build_bvh(rtc_ctx* ctx);
+/* The same on the device: the reference's agglomerative clustering with the merged box's surface area as the distance
+ * (BVH.cs:12-21, 50-191) made data-parallel -- primitives ordered along a Morton curve, every round each cluster picks its
+ * cheapest neighbour within `radius` positions (0 = default 16) and mutual choices merge (PLOC). One primitive per leaf,
+ * exact f64 boxes; rtc_get_bvh returns the tree in the reference's shape. rounds (may be NULL) receives the number of
+ * clustering rounds. */
+int rtc_build_bvh_device(rtc_ctx* ctx, int32_t radius, int32_t* rounds);
 /* Scene.Prepare caches the accelerator on the host (Scene.cs:39-49); the equivalent here is a host-resident image of
  * the device layout (pinned memory), made once from the current scene + BVH and re-uploaded with plain H2D copies at
  * every FullRaytracer.Start(). A baked image belongs to one arithmetic mode. */

@@ -71,6 +71,7 @@ def build(force=False, verbose=False):
         ("kernels_f32.cu", NVCC_COMMON),
         ("kernels_f64.cu", NVCC_COMMON + ["-fmad=false"]),
         ("rtc_api.cu", NVCC_COMMON),
+        ("bvh_build.cu", NVCC_COMMON),
     ]
     for src, flags in units:
         s = os.path.join(CSRC, src)

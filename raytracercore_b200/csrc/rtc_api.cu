@@ -1308,6 +1308,85 @@ int rtc_build_bvh(rtc_ctx* ctx) {
   return finish_bvh(ctx);
 }
 
+int rtc_build_bvh_device(rtc_ctx* ctx, int32_t radius, int32_t* rounds_out) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!ctx->scene_set || (int32_t)ctx->kind.size() != ctx->n_prims) return fail(ctx, RTC_ERR_STATE, "upload the scene before building the BVH");
+  if (ctx->n_prims == 0) return fail(ctx, RTC_ERR_INVALID, "scene has no primitives");
+  if (radius <= 0) radius = 16;
+  rtc_scene_desc d;
+  d.n_prims = ctx->n_prims;
+  d.n_xforms = ctx->n_xforms;
+  d.kind = ctx->kind.data();
+  d.flags = ctx->flags.data();
+  d.geom = ctx->geom.data();
+  d.xform = ctx->xform.data();
+  d.xforms = ctx->xforms.empty() ? nullptr : ctx->xforms.data();
+  d.material = ctx->material.data();
+  const int n = d.n_prims;
+  // leaf boxes exactly as AABB.CreateFromBounded (AABB.cs:20-36); primitives with infinite boxes (planes) stay out of the
+  // clustering and are chained above its root in ID order, like the host builder does
+  std::vector<double> boxes;
+  std::vector<int32_t> ids, unbounded;
+  boxes.reserve((size_t)n * 6);
+  ids.reserve(n);
+  std::vector<double> ub;
+  for (int i = 0; i < n; i++) {
+    double lo[3], hi[3];
+    rtcore::DescPrimitiveBounds(d, i, lo, hi);
+    bool finite = true;
+    for (int k = 0; k < 3; k++) finite = finite && std::isfinite(lo[k]) && std::isfinite(hi[k]);
+    if (finite) {
+      ids.push_back(i);
+      boxes.insert(boxes.end(), lo, lo + 3);
+      boxes.insert(boxes.end(), hi, hi + 3);
+    } else {
+      unbounded.push_back(i);
+      ub.insert(ub.end(), lo, lo + 3);
+      ub.insert(ub.end(), hi, hi + 3);
+    }
+  }
+  const int32_t m = (int32_t)ids.size();
+  std::vector<rtc_bvh_node>& nodes = ctx->nodes;
+  nodes.clear();
+  nodes.resize((m > 0 ? (size_t)2 * m - 1 : 0) + 2 * unbounded.size());
+  int32_t root = -1, rounds = 0, next = 0;
+  cudaSetDevice(ctx->device);
+  if (m > 0) {
+    cudaError_t e = build_bvh_ploc(ctx->stream, m, boxes.data(), ids.data(), radius, nodes.data(), &root, &rounds);
+    if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("build_bvh_ploc: ") + cudaGetErrorString(e));
+    next = 2 * m - 1;
+  }
+  for (size_t j = unbounded.size(); j-- > 0;) {
+    rtc_bvh_node& leaf = nodes[next];
+    std::memset(&leaf, 0, sizeof(leaf));
+    for (int k = 0; k < 3; k++) {
+      leaf.bmin[k] = ub[j * 6 + k];
+      leaf.bmax[k] = ub[j * 6 + 3 + k];
+    }
+    leaf.left = leaf.right = -1;
+    leaf.prim = unbounded[j];
+    if (root < 0) {
+      root = next++;
+      continue;
+    }
+    rtc_bvh_node& par = nodes[next + 1];
+    std::memset(&par, 0, sizeof(par));
+    par.left = next;
+    par.right = root;
+    par.prim = -1;
+    for (int k = 0; k < 3; k++) {
+      par.bmin[k] = std::fmin(leaf.bmin[k], nodes[root].bmin[k]);
+      par.bmax[k] = std::fmax(leaf.bmax[k], nodes[root].bmax[k]);
+    }
+    root = next + 1;
+    next += 2;
+  }
+  nodes.resize(next);
+  ctx->root = root;
+  if (rounds_out) *rounds_out = rounds;
+  return finish_bvh(ctx);
+}
+
 int rtc_bake(rtc_ctx* ctx, rtc_baked** out) {
   if (!ctx || !out) return RTC_ERR_INVALID;
   *out = nullptr;

@@ -212,6 +212,11 @@ struct Kernels {
 cudaError_t launch_overlay_boxcount(cudaStream_t s, const rtc_bvh_node* nodes, int32_t root, const CameraView<double>& cam,
                                     int32_t width, int32_t height, int32_t* out);
 
+// BVH.Construct on the device (bvh_build.cu): parallel locally-ordered clustering over m bounded primitives. boxes: m x
+// (lo[3], hi[3]) f64 on the host, prim_ids: their primitive IDs; nodes_out: 2m-1 nodes (host), leaves first.
+cudaError_t build_bvh_ploc(cudaStream_t stream, int32_t m, const double* boxes, const int32_t* prim_ids, int radius,
+                           rtc_bvh_node* nodes_out, int32_t* root_out, int32_t* rounds_out);
+
 // mode-independent
 cudaError_t launch_tonemap(cudaStream_t s, int32_t n, const double* rgb_sum, const uint32_t* samples,
                            const uint32_t* misses, double exposure, double br, double bg, double bb, double ba,

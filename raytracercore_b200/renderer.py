@@ -79,8 +79,14 @@ class Context:
     def upload_bvh(self, nodes, n_nodes, root):
         self._ck(N.lib.rtc_upload_bvh(self._h, n_nodes, nodes, root))
 
-    def build_bvh(self):
-        self._ck(N.lib.rtc_build_bvh(self._h))
+    def build_bvh(self, device=False, radius=0):
+        """Host binned-SAH build, or (device=True) the clustering build on the GPU; returns its number of rounds."""
+        if not device:
+            self._ck(N.lib.rtc_build_bvh(self._h))
+            return 0
+        rounds = C.c_int32()
+        self._ck(N.lib.rtc_build_bvh_device(self._h, radius, C.byref(rounds)))
+        return rounds.value
 
     def get_bvh(self):
         n = C.c_int32()
@@ -106,10 +112,13 @@ class Context:
         self._ck(N.lib.rtc_set_params(self._h, C.byref(par)))
         self.width, self.height = par.width, par.height
 
-    def load(self, scene, seed=1, camera=None, use_scene_bvh=True):
-        """Scene.Prepare + FullRaytracer.Start's set-up (FullRaytracer.cs:253-269) in one call."""
+    def load(self, scene, seed=1, camera=None, use_scene_bvh=True, device_bvh=False, radius=0):
+        """Scene.Prepare + FullRaytracer.Start's set-up (FullRaytracer.cs:253-269) in one call. device_bvh: build the
+        tree on the GPU (rtc_build_bvh_device) instead of taking the host scene's accelerator."""
         self.upload_scene(scene)
-        if use_scene_bvh:
+        if device_bvh:
+            self.build_bvh(device=True, radius=radius)
+        elif use_scene_bvh:
             nodes, n, root = scene.bvh()
             self.upload_bvh(nodes, n, root)
         else:

@@ -232,3 +232,72 @@ def test_vertex_normal_triangles_keep_the_reference_quirks():
         assert np.allclose(got["normal"][front], want["normal"][front], atol=tol)
         assert np.isnan(want["normal"][back]).all() and np.isnan(got["normal"][back]).all()
         ctx.close()
+
+
+def _tree_as_array(ctx):
+    nodes, n, root = ctx.get_bvh()
+    dt = np.dtype([("bmin", "<f8", 3), ("bmax", "<f8", 3), ("left", "<i4"), ("right", "<i4"), ("prim", "<i4"), ("pad", "<i4")])
+    import ctypes as C
+    return np.frombuffer((N.BvhNode * n).from_buffer_copy(nodes), dtype=dt).copy(), root
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("make", ["mixed", "cornell", "soup", "duplicates", "single", "planes"])
+def test_device_built_tree_is_valid_and_traces_like_the_host_tree(make):
+    """rtc_build_bvh_device (the reference's surface-area clustering, data-parallel): a reference-shaped tree -- one
+    primitive per leaf, leaf boxes = AABB.CreateFromBounded, inner boxes = exact unions -- and, because a closest hit does
+    not depend on the topology, the same hits as the host-built tree in the bit-exact f64 mode."""
+    if make == "mixed":
+        sc = Scene.from_string(MIXED)
+    elif make == "cornell":
+        sc = Scene.from_file(os.path.join(SCENES, "cornell_bounce.scene"))
+    elif make == "soup":
+        sc = Scene.synthetic("soup", 30000, 11, 0.03)
+    elif make == "duplicates":  # 600 identical triangles + 1: every candidate pair costs the same
+        tri = "vertex 0 0 0\nvertex 1 0 0\nvertex 0 1 0\nvertex 5 5 5\nvertex 6 5 5\nvertex 5 6 5\n" + "tri 0 1 2\n" * 600 + "tri 3 4 5\n"
+        sc = Scene.from_string("size 8 8\ncamera 0 0 -5 0 0 0 0 1 0 40\ntwosided true\n" + tri)
+    elif make == "single":
+        sc = Scene.from_string("size 8 8\ncamera 0 0 -5 0 0 0 0 1 0 40\ntwosided true\nsphere 0 0 0 1\n")
+    else:
+        sc = Scene.from_string("size 8 8\ncamera 0 0 -5 0 0 0 0 1 0 40\ntwosided true\nplane 1 0 0 1\nplane 0 1 0 2\n")
+    n = sc.n_prims
+    dev = Context(0, RTC_F64)
+    dev.upload_scene(sc)
+    rounds = dev.build_bvh(device=True, radius=8)
+    nodes, root = _tree_as_array(dev)
+    assert len(nodes) == 2 * n - 1
+    bounded = sum(1 for i in range(n) if np.isfinite(np.concatenate(sc.primitive_bounds(i))).all())
+    assert (rounds >= 1) == (bounded > 1) and rounds <= 200
+    seen = np.zeros(n, bool)
+    stack, visited = [root], 0
+    while stack:
+        nd = nodes[stack.pop()]
+        visited += 1
+        if nd["prim"] >= 0:
+            assert nd["left"] == -1 and nd["right"] == -1 and not seen[nd["prim"]]
+            seen[nd["prim"]] = True
+            lo, hi = sc.primitive_bounds(int(nd["prim"]))  # (the flattened description's bounds: last-bit differences allowed)
+            assert np.allclose(lo, nd["bmin"], rtol=1e-14, atol=1e-12, equal_nan=True) and np.allclose(hi, nd["bmax"], rtol=1e-14, atol=1e-12, equal_nan=True)
+        else:
+            l, r = nodes[nd["left"]], nodes[nd["right"]]
+            assert np.array_equal(nd["bmin"], np.minimum(l["bmin"], r["bmin"])) and np.array_equal(nd["bmax"], np.maximum(l["bmax"], r["bmax"]))
+            stack += [int(nd["left"]), int(nd["right"])]
+    assert seen.all() and visited == len(nodes)
+    host = Context(0, RTC_F64)
+    host.upload_scene(sc)
+    host.upload_bvh(*sc.bvh())
+    rays = random_rays(np.random.default_rng(5), 20000, -2.5, 2.5, RAY_DT)
+    a, b = dev.trace_closest(rays), host.trace_closest(rays)
+    same = (a["prim"] == b["prim"]) & (a["inside"] == b["inside"])
+    if make == "duplicates":  # coincident triangles: which of the 600 answers is a tie the two trees may break differently
+        same |= (a["prim"] >= 0) & (b["prim"] >= 0) & (a["prim"] < 600) & (b["prim"] < 600)
+    assert same.all()
+    hit = a["prim"] >= 0
+    assert np.array_equal(a["t"][hit], b["t"][hit])
+    # and the f32 production mode renders through the device-built tree
+    f32 = Context(0, RTC_F32)
+    f32.load(sc, seed=2, device_bvh=True)
+    h32 = f32.trace_closest(rays)
+    assert ((h32["prim"] >= 0) == hit).mean() > 0.999
+    for c in (dev, host, f32):
+        c.close()

@@ -19,6 +19,7 @@ ap.add_argument("--size", type=int, default=0, help="override width=height")
 ap.add_argument("--precision", default="f32")
 ap.add_argument("--counters", action="store_true")
 ap.add_argument("--max-paths", type=int, default=0)
+ap.add_argument("--device-bvh", type=int, default=-1, help="build the tree on the GPU with this search radius (0 = default)")
 a = ap.parse_args()
 sc = bench.make_scene(a.workload)
 if a.size:
@@ -26,7 +27,23 @@ if a.size:
 ctx = Context(0, RTC_F64 if a.precision == "f64" else RTC_F32)
 if a.max_paths:
     ctx.set_option(RTC_OPT_MAX_PATHS, a.max_paths)
-ctx.load(sc, seed=1)
+t_build = time.time()
+if a.device_bvh >= 0:
+    ctx.upload_scene(sc)
+    t_build = time.time()
+    rounds = ctx.build_bvh(device=True, radius=a.device_bvh)
+    print("device BVH build + flatten + upload: %.3f s (%d rounds, radius %d)" % (time.time() - t_build, rounds, a.device_bvh))
+    ctx.set_params(sc.params(1))
+    ctx.set_camera(sc.camera(None))
+else:
+    nodes, n, root = sc.bvh()
+    print("host BVH build: %.3f s" % (time.time() - t_build))
+    t_build = time.time()
+    ctx.upload_scene(sc)
+    ctx.upload_bvh(nodes, n, root)
+    print("flatten + upload: %.3f s" % (time.time() - t_build))
+    ctx.set_params(sc.params(1))
+    ctx.set_camera(sc.camera(None))
 ctx.render(0, a.spp)
 ctx.sync()
 ctx.reset_stats()
