@@ -292,7 +292,7 @@ SceneView<R> scene_view(rtc_ctx* c) {
   sv.qnodes = (const CNode*)c->d_qnodes;
   sv.unbounded = c->d_unbounded;
   sv.n_unbounded = c->n_unbounded;
-  sv.q_stack = std::max(2, c->bvh_depth + 1);
+  sv.q_stack = std::max(2, c->bvh_depth + (c->precision == RTC_F64 ? 2 : 1));  // f64: the binary tree's stack need + 2
   return sv;
 }
 

@@ -846,15 +846,47 @@ struct TraceIO {
 constexpr int kRefill = RTC_REFILL;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
+// The f64 kernel's traversal stack: (node, box near) pairs in dynamic shared memory, one column per thread
+// ([entry][thread] nodes, then [entry][thread] nears), sized per scene to the tree's depth -- a per-thread array would live
+// in local memory (1.5 KB per thread, every push and pop a trip through L1).
 template <typename R>
-__device__ __forceinline__ void stack_pop(const uint32_t* stack_node, const R* stack_near, int& sp, R best_t, uint32_t& cur,
-                                          R& cur_near) {
+struct TraceStack {
+  uint32_t node_at, near_at;  // shared-window byte addresses of this thread's entry 0
+  __device__ __forceinline__ void init(uint32_t base, int entries) {
+    node_at = base + threadIdx.x * 4u;
+    near_at = base + (uint32_t)entries * kTraceThreads * 4u + threadIdx.x * (uint32_t)sizeof(R);
+  }
+  __device__ __forceinline__ void push(int sp, uint32_t node, R nr) const {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(node_at + (uint32_t)sp * kTraceThreads * 4u), "r"(node));
+    if constexpr (sizeof(R) == 8)
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(near_at + (uint32_t)sp * kTraceThreads * 8u), "d"(nr));
+    else
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(near_at + (uint32_t)sp * kTraceThreads * 4u), "f"(nr));
+  }
+  __device__ __forceinline__ uint32_t node(int sp) const {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(node_at + (uint32_t)sp * kTraceThreads * 4u));
+    return v;
+  }
+  __device__ __forceinline__ R nearv(int sp) const {
+    R v;
+    if constexpr (sizeof(R) == 8)
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(near_at + (uint32_t)sp * kTraceThreads * 8u));
+    else
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(near_at + (uint32_t)sp * kTraceThreads * 4u));
+    return v;
+  }
+};
+
+template <typename R>
+__device__ __forceinline__ void stack_pop(const TraceStack<R>& stk, int& sp, R best_t, uint32_t& cur, R& cur_near) {
   cur = kNone;
   while (sp > 0) {
     sp--;
-    if (!(stack_near[sp] > best_t)) {
-      cur = stack_node[sp];
-      cur_near = stack_near[sp];
+    const R nr = stk.nearv(sp);
+    if (!(nr > best_t)) {
+      cur = stk.node(sp);
+      cur_near = nr;
       break;
     }
   }
@@ -866,8 +898,9 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   uint32_t n_nodes = 0, n_prims = 0;
-  uint32_t stack_node[kTraceStack];
-  R stack_near[kTraceStack];
+  extern __shared__ uint2 s_stack[];
+  TraceStack<R> stk;
+  stk.init((uint32_t)__cvta_generic_to_shared(s_stack), sc.q_stack);
   bool active = false;      // the lane holds an unfinished ray
   bool finished = false;    // the lane holds a finished ray whose Hit record is not written yet
   bool exhausted = false;   // warp-uniform: the queue has no more entries
@@ -1000,8 +1033,7 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
               asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
             }
 #endif
-            stack_node[sp] = ch[c];
-            stack_near[sp] = key[c];
+            stk.push(sp, ch[c], key[c]);
             sp++;
           }
         }
@@ -1009,7 +1041,7 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
           cur = ch[0];
           cur_near = key[0];
         } else {
-          stack_pop<R>(stack_node, stack_near, sp, best.t, cur, cur_near);
+          stack_pop<R>(stk, sp, best.t, cur, cur_near);
         }
       }
     } else {
@@ -1017,7 +1049,7 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
       if (active && (cur & REF_LEAF)) {
         if (COUNT) n_prims++;
         test_leaf<R>(sc, cur, load_prim(sc, cur & REF_SLOT_MASK), cur_near, o, d, sk, src, path, best);
-        stack_pop<R>(stack_node, stack_near, sp, best.t, cur, cur_near);
+        stack_pop<R>(stk, sp, best.t, cur, cur_near);
       }
     }
     if (active && cur == kNone) {
@@ -1666,7 +1698,7 @@ template <typename R>
 int Kernels<R>::trace_blocks_per_sm(size_t smem) {
   int nb = 0;
   if constexpr (Num<R>::is_f64)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<R, false>, kTraceThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<R, false>, kTraceThreads, smem);
   else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_q8<false>, kTraceThreads, smem);
   return nb > 0 ? nb : 1;
@@ -1690,10 +1722,15 @@ cudaError_t Kernels<R>::camera_rays(const LaunchCfg& cfg, const CameraView<R>& c
 template <typename R>
 cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, int prev, int cur,
                               bool identity_queue) {
-  const size_t smem = Num<R>::is_f64 ? 0 : (size_t)sc.q_stack * kTraceThreads * sizeof(uint2) + kQ8StateWords * kTraceThreads * sizeof(float);
+  const size_t smem = Num<R>::is_f64 ? (size_t)sc.q_stack * kTraceThreads * (4 + sizeof(R))
+                                     : (size_t)sc.q_stack * kTraceThreads * sizeof(uint2) + kQ8StateWords * kTraceThreads * sizeof(float);
   static thread_local size_t per_sm_smem = ~(size_t)0;  // resident CTAs per SM for the stack size last seen (persistent grid = all of them)
   static thread_local int per_sm = 1;
   if (smem != per_sm_smem) {
+    if constexpr (Num<R>::is_f64) {  // deep binary trees need more than the default 48 KB of dynamic shared memory
+      cudaFuncSetAttribute(k_trace<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_trace<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     per_sm = trace_blocks_per_sm(smem);
     if (const char* cap = std::getenv("RTC_TRACE_BLOCKS_PER_SM"))  // tuning aid: fewer resident CTAs than fit
       per_sm = std::max(1, std::min(per_sm, std::atoi(cap)));
@@ -1712,9 +1749,9 @@ cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, cons
   io.ctl = pv.ctl;
   if constexpr (Num<R>::is_f64) {
     if (cfg.counters)
-      k_trace<R, true><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, io);
+      k_trace<R, true><<<grid, kTraceThreads, smem, cfg.stream>>>(sc, io);
     else
-      k_trace<R, false><<<grid, kTraceThreads, 0, cfg.stream>>>(sc, io);
+      k_trace<R, false><<<grid, kTraceThreads, smem, cfg.stream>>>(sc, io);
   } else {
     if (cfg.counters)
       k_trace_q8<true><<<grid, kTraceThreads, smem, cfg.stream>>>(sc, io);

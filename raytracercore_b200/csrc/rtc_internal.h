@@ -122,7 +122,7 @@ struct SceneView {
   const CNode* qnodes;     // f32 mode only: the quantised 8-wide tree over the bounded primitives
   const uint32_t* unbounded;  // f32 mode only: leaf references of primitives with infinite boxes (planes)
   int32_t n_unbounded;
-  int32_t q_stack;         // f32 mode only: traversal stack entries per lane (tree depth + 1)
+  int32_t q_stack;         // traversal stack entries per lane (f32: 8-wide tree depth + 1; f64: binary tree's need + 2)
 };
 
 template <typename R>
