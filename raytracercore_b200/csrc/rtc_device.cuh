@@ -1727,9 +1727,12 @@ cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, cons
   static thread_local size_t per_sm_smem = ~(size_t)0;  // resident CTAs per SM for the stack size last seen (persistent grid = all of them)
   static thread_local int per_sm = 1;
   if (smem != per_sm_smem) {
-    if constexpr (Num<R>::is_f64) {  // deep binary trees need more than the default 48 KB of dynamic shared memory
+    if constexpr (Num<R>::is_f64) {  // deep trees need more than the default 48 KB of dynamic shared memory
       cudaFuncSetAttribute(k_trace<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cudaFuncSetAttribute(k_trace<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    } else if (smem > 48 * 1024) {
+      cudaFuncSetAttribute(k_trace_q8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_trace_q8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     per_sm = trace_blocks_per_sm(smem);
     if (const char* cap = std::getenv("RTC_TRACE_BLOCKS_PER_SM"))  // tuning aid: fewer resident CTAs than fit

@@ -301,3 +301,40 @@ def test_device_built_tree_is_valid_and_traces_like_the_host_tree(make):
     assert ((h32["prim"] >= 0) == hit).mean() > 0.999
     for c in (dev, host, f32):
         c.close()
+
+
+@pytest.mark.gpu
+def test_degenerate_chain_tree():
+    """A hand-made chain (every inner node = one leaf + the rest) over a lattice of 320 spheres: the deepest tree the f32 mode accepts.
+    Its collapsed 8-wide form is ~46 levels deep, so the shared-memory stack exceeds the default 48 KB; the f64 mode
+    refuses the tree (its stack bound is 126 entries) with RTC_ERR_UNSUPPORTED -- never a wrong answer."""
+    n = 320
+    text = "size 8 8\ncamera 0 0 -50 0 0 0 0 1 0 40\ntwosided true\n" + "".join(
+        "sphere %.1f %.1f %.1f 0.1\n" % (0.3 * (i % 7), 0.3 * ((i // 7) % 7), 0.3 * (i // 49)) for i in range(n))  # a 7x7x7 lattice
+    sc = Scene.from_string(text)
+    nodes = (N.BvhNode * (2 * n - 1))()
+    for i in range(n):
+        lo, hi = sc.primitive_bounds(i)
+        nodes[i].bmin[:], nodes[i].bmax[:] = list(lo), list(hi)
+        nodes[i].left, nodes[i].right, nodes[i].prim = -1, -1, i
+    for j in range(n - 2, -1, -1):  # inner node n + j = (leaf j, inner n + j + 1 | last leaf)
+        k, r = n + j, (n + j + 1 if j < n - 2 else n - 1)
+        nodes[k].left, nodes[k].right, nodes[k].prim = j, r, -1
+        nodes[k].bmin[:] = [min(nodes[j].bmin[a], nodes[r].bmin[a]) for a in range(3)]
+        nodes[k].bmax[:] = [max(nodes[j].bmax[a], nodes[r].bmax[a]) for a in range(3)]
+    ora = O.OracleScene(sc)
+    rng = np.random.default_rng(3)
+    rays = random_rays(rng, 4096, -0.5, 2.5, RAY_DT)
+    want = ora.trace_closest(rays)
+    assert (want["prim"] >= 0).mean() > 0.2
+    for prec, tol, exact in MODES:
+        ctx = Context(0, prec)
+        ctx.upload_scene(sc)
+        try:
+            ctx.upload_bvh(nodes, 2 * n - 1, n)
+        except RtcError as e:
+            assert prec == RTC_F64 and e.code == N.RTC_ERR_UNSUPPORTED
+            ctx.close()
+            continue
+        check_hits(ctx.trace_closest(rays), want, tol, exact, origins=rays["origin"], dirs=rays["dir"])
+        ctx.close()
