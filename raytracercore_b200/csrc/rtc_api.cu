@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -420,8 +421,27 @@ int upload_baked_image(rtc_ctx* ctx, const rtc_baked* bk) {
 }
 
 // Flatten the reference-shaped tree + primitives into the device layout (see rtc_internal.h).
+// RTC_B200_VERBOSE: wall-clock of the phases of build_device_scene
+struct PhaseTimer {
+  bool on = std::getenv("RTC_B200_VERBOSE") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  std::string log;
+  void mark(const char* name) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    char buf[96];
+    std::snprintf(buf, sizeof(buf), " %s %.0f ms,", name, std::chrono::duration<double, std::milli>(now - t).count());
+    log += buf;
+    t = now;
+  }
+  ~PhaseTimer() {
+    if (on && !log.empty()) std::fprintf(stderr, "[rtcore_b200] flatten:%s\n", log.c_str());
+  }
+};
+
 template <typename R>
 int build_device_scene(rtc_ctx* ctx) {
+  PhaseTimer pt;
   const int32_t n = ctx->n_prims;
   const int32_t nn = (int32_t)ctx->nodes.size();
   const std::vector<rtc_bvh_node>& nodes = ctx->nodes;
@@ -608,6 +628,7 @@ int build_device_scene(rtc_ctx* ctx) {
       }
       return i;
     };
+    pt.mark("validate + boxes");
     // Optimal collapse (after Ylitie, Karras & Laine 2017, sec. 3): T(m, i) = least total surface area of the wide nodes
     // needed below binary node m when m's subtree may occupy at most i child slots of its parent wide node. A leaf costs
     // nothing; an inner node either becomes a wide node itself (its area + its two sides spread over 8 slots) or hands
@@ -683,6 +704,7 @@ int build_device_scene(rtc_ctx* ctx) {
         stack_[sp_++] = {resolve(nd.left), k, false};
       }
     };
+    pt.mark("collapse DP");
     const int32_t n_bounded = nf[ctx->root];
     int32_t next_slot = 0;
     int32_t max_depth = 0;
@@ -835,6 +857,7 @@ int build_device_scene(rtc_ctx* ctx) {
     ctx->root_node = 0;
   }
 
+  pt.mark("node emission");
   std::vector<DPrim<R>> dp(n);
   std::vector<DMat<R>> dm(n);
   std::vector<int32_t> aux(n, -1), prim_id(n), id_to_slot(n);
@@ -891,6 +914,7 @@ int build_device_scene(rtc_ctx* ctx) {
     }
   }
 
+  pt.mark("primitive + material records");
   rtc_baked* bk = new rtc_baked();
   bk->precision = ctx->precision;
   bk->n_prims = n;
@@ -918,7 +942,11 @@ int build_device_scene(rtc_ctx* ctx) {
     if (sz[i]) std::memcpy(bk->host + bk->off[i], src[i], sz[i]);
   delete ctx->baked;
   ctx->baked = bk;
-  return upload_baked_image(ctx, bk);
+  pt.mark("pinned image");
+  const int rc_up = upload_baked_image(ctx, bk);
+  if (pt.on) cudaStreamSynchronize(ctx->stream);
+  pt.mark("upload");
+  return rc_up;
 }
 
 int ready(rtc_ctx* ctx, bool need_camera) {
