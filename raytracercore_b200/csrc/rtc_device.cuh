@@ -66,7 +66,9 @@ __device__ __forceinline__ float rpow(float a, float b) { return powf(a, b); }
 __device__ __forceinline__ double rpow(double a, double b) { return pow(a, b); }
 __device__ __forceinline__ float racos(float a) { return acosf(a); }
 __device__ __forceinline__ double racos(double a) { return acos(a); }
-__device__ __forceinline__ void rsincos(float a, float* s, float* c) { sincosf(a, s, c); }
+// f32: the angles are u * 2 pi with u in [0, 1); sincospif has no large-argument slow path (sincosf carries a Payne-Hanek
+// reduction with a local-memory table that is never needed here)
+__device__ __forceinline__ void rsincos(float a, float* s, float* c) { sincospif(a * 0.31830988618379067f, s, c); }
 __device__ __forceinline__ void rsincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
 __device__ __forceinline__ bool rsignbit(float a) { return (__float_as_uint(a) >> 31) != 0; }
 __device__ __forceinline__ bool rsignbit(double a) { return (__double_as_longlong(a) < 0); }
@@ -769,6 +771,9 @@ constexpr int kStreamThreads = 256;
 #ifndef RTC_TRACE_MIN_BLOCKS
 #define RTC_TRACE_MIN_BLOCKS 8
 #endif
+#ifndef RTC_SHADE_MIN_BLOCKS
+#define RTC_SHADE_MIN_BLOCKS 3
+#endif
 #ifndef RTC_PREFETCH
 #define RTC_PREFETCH 0
 #endif
@@ -1359,7 +1364,7 @@ __device__ __forceinline__ R luminance(R r, R g, R b) { return (R(0.299) * r + R
 // radiance; the survivors overwrite dir/tint in place and are appended to the next bounce's queue by a warp-aggregated
 // stream compaction (ballot + popc + one atomicAdd per warp) -- the loop's `break`/`return` of the reference.
 template <typename R>
-__global__ void __launch_bounds__(kStreamThreads) k_shade(SceneView<R> sc, ParamsView<R> par, Band band, PathView<R> pv, int q,
+__global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(SceneView<R> sc, ParamsView<R> par, Band band, PathView<R> pv, int q,
                                                            int cur, int bounce, int identity_queue) {
   const uint32_t count = pv.ctl->count[q];
   const uint32_t* queue = q ? pv.queue[1] : pv.queue[0];
