@@ -132,7 +132,7 @@ struct rtc_ctx {
   rtc_baked* baked = nullptr;               // image of the current device scene
 
   // path pool
-  int64_t max_paths = 1 << 23;
+  int64_t max_paths = 1 << 25;
   int64_t pool_cap = 0;
   void *d_dir = nullptr, *d_tint = nullptr, *d_hpos[2] = {nullptr, nullptr}, *d_hnrm[2] = {nullptr, nullptr},
        *d_radiance = nullptr, *d_skip_pos = nullptr;
@@ -240,8 +240,12 @@ void free_pool(rtc_ctx* c) {
   c->pool_cap = 0;
 }
 
+// The pool holds what the largest wavefront so far needed (at most RTC_OPT_MAX_PATHS paths): it only grows, in 64 Ki steps.
 int ensure_pool(rtc_ctx* ctx, int64_t want) {
+  want = std::max<int64_t>(want, 1024);
   if (ctx->pool_cap >= want && ctx->d_dir) return RTC_OK;
+  want = (want + 65535) & ~(int64_t)65535;
+  CU(cudaStreamSynchronize(ctx->stream));
   free_pool(ctx);
   size_t v4 = rsize(ctx) * 4;
   CU(cudaMalloc(&ctx->d_dir, v4 * want));
@@ -1059,7 +1063,7 @@ int render_rect(rtc_ctx* ctx, int x0, int y0, int x1, int y1, uint32_t first_sam
                 double* d_out_rgb, const ReadBack* rb = nullptr) {
   const int64_t rw = x1 - x0;
   const int64_t cap = std::max<int64_t>(ctx->max_paths, rw);
-  int rc = ensure_pool(ctx, cap);
+  int rc = ensure_pool(ctx, std::min<int64_t>(cap, rw * (int64_t)(y1 - y0) * (int64_t)n_samples));
   if (rc) return rc;
   int64_t rows_per_band = std::max<int64_t>(1, std::min<int64_t>(y1 - y0, cap / rw));
   for (int ya = y0; ya < y1; ya += (int)rows_per_band) {
@@ -1109,7 +1113,7 @@ int ensure_accum(rtc_ctx* ctx) {
 template <typename R>
 int trace_batch(rtc_ctx* ctx, int64_t n, const rtc_ray* rays, const rtc_hit* skip, rtc_hit* out) {
   const int64_t cap = ctx->max_paths;
-  int rc = ensure_pool(ctx, cap);
+  int rc = ensure_pool(ctx, std::min(cap, n));
   if (rc) return rc;
   if (!ctx->d_skip_pos) CU(cudaMalloc(&ctx->d_skip_pos, rsize(ctx) * 4 * ctx->pool_cap));
   if (ctx->stage_cap < std::min(cap, n)) {
@@ -1690,7 +1694,7 @@ int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t
   cudaSetDevice(ctx->device);
   rc = wait_shading_upload(ctx);
   if (rc) return rc;
-  rc = ensure_pool(ctx, ctx->max_paths);
+  rc = ensure_pool(ctx, 1024);
   if (rc) return rc;
   if (!ctx->d_dbg_type) {
     CU(cudaMalloc((void**)&ctx->d_dbg_type, sizeof(int32_t) * 32));
@@ -1785,7 +1789,7 @@ int rtc_debug_raycast(rtc_ctx* ctx, int32_t mode, int32_t* out) {
     auto run = [&](auto tag) -> int {
       using R = decltype(tag);
       const int64_t cap = std::max<int64_t>(ctx->max_paths, w);
-      int rc2 = ensure_pool(ctx, cap);
+      int rc2 = ensure_pool(ctx, std::min<int64_t>(cap, (int64_t)w * h));
       if (rc2) return rc2;
       LaunchCfg cfg{ctx->stream, ctx->sm_count, false};
       SceneView<R> sv = scene_view<R>(ctx);
