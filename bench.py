@@ -23,17 +23,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# spp = samples per pixel per step and GPU, chosen so that one step is one wavefront of up to 32 Mi paths (the pool's cap):
+# ~65 ms per step on the 1 M-triangle scene, the order of the reference's 100 ms status / bitmap cadence (FullRaytracer.cs:33,369).
 WORKLOADS = {
     # name: (description, builder kwargs)
     "soup1m": dict(desc="synthetic 1M-triangle random soup, 2048x2048, recursion 4 (BASELINE C3)", synth="soup", n=1_000_000,
-                   seed=0xC3, jitter=0.01, width=2048, height=2048, recursion=4, spp=4),
+                   seed=0xC3, jitter=0.01, width=2048, height=2048, recursion=4, spp=8),
     "soup10m": dict(desc="synthetic 10M-triangle random soup, 3840x2160, recursion 4 (BASELINE C5)", synth="soup", n=10_000_000,
-                    seed=0xC5, jitter=0.004, width=3840, height=2160, recursion=4, spp=2),
+                    seed=0xC5, jitter=0.004, width=3840, height=2160, recursion=4, spp=4),
     "spheres100k": dict(desc="synthetic 100k spheres mirror/glass/diffuse, 1920x1080, recursion 8 (BASELINE C4)", synth="spheres",
-                        n=100_000, seed=0xC4, jitter=0.0, width=1920, height=1080, recursion=8, spp=4),
-    "die": dict(desc="die scene 1920x1080, recursion 3, DOF (BASELINE C2)", file="die.scene", width=1920, height=1080, recursion=3, spp=4),
+                        n=100_000, seed=0xC4, jitter=0.0, width=1920, height=1080, recursion=8, spp=16),
+    "die": dict(desc="die scene 1920x1080, recursion 3, DOF (BASELINE C2)", file="die.scene", width=1920, height=1080, recursion=3, spp=16),
     "bounce": dict(desc="Cornell 'bounce' scene 512x512, recursion 8 (BASELINE C1)", file="cornell_bounce.scene", width=512, height=512,
-                   recursion=8, spp=32),
+                   recursion=8, spp=128),
 }
 
 
