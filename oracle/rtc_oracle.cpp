@@ -6,7 +6,8 @@
 // places where an FMA is used below are the AVX path's. Build with -ffp-contract=off: every fused operation
 // in this file is an explicit std::fma.
 //
-// PARITY UNPINNED by the reference (it has no tests/golden vectors and cannot run here); see rtc_oracle.h.
+// Pinned against the reference's two published renders (tests/test_screenshots.py) and analytic known answers; per-ray
+// quantities remain UNPINNED by the reference (it has no tests / golden vectors and cannot run here); see rtc_oracle.h.
 
 #include "rtc_oracle.h"
 
