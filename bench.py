@@ -351,12 +351,13 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = (float(st.rays) * bpr / 1e9) / (trace_ms * 1e-3) if trace_ms > 0 else None
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_trace_q8, mean of the three launches captured with
-        # `ncu --set full` in profiles/r1d_trace_q8_ncu_full.csv (soup1m, f32); null for workloads without a capture
-        traffic = 0.4710e9 if (args.workload == "soup1m" and args.precision == "f32") else None
+        # dram__bytes_read.sum + dram__bytes_write.sum of k_trace_q8 from the `ncu --set full` capture in
+        # profiles/r1d_trace_q8_ncu_full.csv (soup1m, f32): 364.2 / 495.7 / 553.2 MB for launches of 4 194 304 / 3 933 350 /
+        # 2 529 048 rays = 132.6 B per ray, scaled to this run's rays per launch; null for workloads without a capture
+        traffic = 132.6 * float(st.rays) / max(1, trace_launches) if (args.workload == "soup1m" and args.precision == "f32") else None
         roofline = {"bound": "hbm", "kernel": "k_trace_q8" if args.precision == "f32" else "k_trace<double>", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                    "traffic_source": "profiles/r1d_trace_q8_ncu_full.csv (bytes per launch; L2-resident tree: traffic << algorithmic bytes)" if traffic else None,
+                    "traffic_source": "profiles/r1d_trace_q8_ncu_full.csv: 132.6 B of DRAM traffic per ray x rays_per_launch (L2-resident tree: traffic << algorithmic bytes)" if traffic else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_ray": bpr, "rays_per_launch": float(st.rays) / max(1, trace_launches),
                     "avg_launch_ms": trace_ms / max(1, trace_launches),

@@ -1,7 +1,7 @@
 """Turns raw ncu output (brought back in gpurun_out/) into the small CSV summaries committed under profiles/.
 
-  python tools/ncu_summaries.py launches gpurun_out/r1c_launches.csv profiles/r1c_launch_summary.csv
-  python tools/ncu_summaries.py full gpurun_out/r1c_trace.ncu-rep profiles/r1c_trace_q8_ncu_full.csv
+  python tools/ncu_summaries.py launches gpurun_out/r1d_launches.csv profiles/r1d_launch_summary.csv
+  python tools/ncu_summaries.py full gpurun_out/r1d_trace.ncu-rep profiles/r1d_trace_q8_ncu_full.csv
 """
 import csv
 import io
