@@ -1729,9 +1729,14 @@ cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, cons
                               bool identity_queue) {
   const size_t smem = Num<R>::is_f64 ? (size_t)sc.q_stack * kTraceThreads * (4 + sizeof(R))
                                      : (size_t)sc.q_stack * kTraceThreads * sizeof(uint2) + kQ8StateWords * kTraceThreads * sizeof(float);
-  static thread_local size_t per_sm_smem = ~(size_t)0;  // resident CTAs per SM for the stack size last seen (persistent grid = all of them)
-  static thread_local int per_sm = 1;
-  if (smem != per_sm_smem) {
+  // resident CTAs per SM for the (device, stack size) last seen (persistent grid = all of them); function attributes are
+  // per device, so a change of device re-applies them
+  static thread_local size_t per_sm_smem = ~(size_t)0;
+  static thread_local int per_sm = 1, per_sm_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem != per_sm_smem || dev != per_sm_dev) {
+    per_sm_dev = dev;
     if constexpr (Num<R>::is_f64) {  // deep trees need more than the default 48 KB of dynamic shared memory
       cudaFuncSetAttribute(k_trace<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cudaFuncSetAttribute(k_trace<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
