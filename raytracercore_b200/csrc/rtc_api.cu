@@ -1066,6 +1066,7 @@ int render_rect(rtc_ctx* ctx, int x0, int y0, int x1, int y1, uint32_t first_sam
   int rc = ensure_pool(ctx, std::min<int64_t>(cap, rw * (int64_t)(y1 - y0) * (int64_t)n_samples));
   if (rc) return rc;
   int64_t rows_per_band = std::max<int64_t>(1, std::min<int64_t>(y1 - y0, cap / rw));
+  if (rows_per_band >= 4) rows_per_band &= ~(int64_t)3;  // whole 8 x 4 pixel tiles per band (band_pix_xy)
   for (int ya = y0; ya < y1; ya += (int)rows_per_band) {
     int yb = (int)std::min<int64_t>(y1, ya + rows_per_band);
     int64_t npix = rw * (yb - ya);

@@ -751,13 +751,28 @@ __device__ __forceinline__ void get_camera_ray(const CameraView<R>& c, const Par
   }
 }
 
+// Band-local pixel index -> pixel. Pixels are numbered tile by tile, 8 x 4 pixels per tile, so that the 32 camera rays of a
+// warp cover a compact patch of the image instead of a 32 x 1 strip (closer rays fetch the same nodes: fewer L1 wavefronts);
+// a band whose width or height is no multiple of the tile falls back to row-major order. The Philox counter uses the
+// pixel's own coordinates, so the image does not depend on this numbering.
+__device__ __forceinline__ void band_pix_xy(const Band& b, uint32_t pix, int& x, int& y) {
+  const uint32_t rw = (uint32_t)(b.x1 - b.x0), rh = (uint32_t)(b.y1 - b.y0);
+  if (((rw & 7u) | (rh & 3u)) == 0) {
+    const uint32_t tile = pix >> 5, in = pix & 31u, tiles_per_row = rw >> 3;
+    const uint32_t ty = tile / tiles_per_row, tx = tile - ty * tiles_per_row;
+    x = b.x0 + (int)(tx * 8u + (in & 7u));
+    y = b.y0 + (int)(ty * 4u + (in >> 3));
+  } else {
+    const uint32_t py = pix / rw;
+    x = b.x0 + (int)(pix - py * rw);
+    y = b.y0 + (int)py;
+  }
+}
+
 __device__ __forceinline__ void band_pixel(const Band& b, uint32_t path, int& x, int& y, uint32_t& sample) {
   uint32_t s_local = path / b.n_pix;
   uint32_t pix = path - s_local * b.n_pix;
-  uint32_t rw = (uint32_t)(b.x1 - b.x0);
-  uint32_t py = pix / rw;
-  x = b.x0 + (int)(pix - py * rw);
-  y = b.y0 + (int)py;
+  band_pix_xy(b, pix, x, y);
   sample = b.first_sample + s_local;
 }
 
@@ -1560,9 +1575,9 @@ __global__ void __launch_bounds__(kStreamThreads) k_accumulate(ParamsView<R> par
                                                                 uint32_t* samples, uint32_t* misses) {
   uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= band.n_pix) return;
-  uint32_t rw = (uint32_t)(band.x1 - band.x0);
-  uint32_t py = pix / rw;
-  size_t g = (size_t)(band.y0 + (int)py) * par.width + (band.x0 + (int)(pix - py * rw));
+  int px, py;
+  band_pix_xy(band, pix, px, py);
+  size_t g = (size_t)py * par.width + px;
   double r = rgb_sum[g * 3 + 0], gg = rgb_sum[g * 3 + 1], b = rgb_sum[g * 3 + 2];
   uint32_t ns = samples[g], nm = misses[g];
   for (uint32_t s = 0; s < band.n_samples; s++) {
@@ -1650,9 +1665,9 @@ template <typename R>
 __global__ void __launch_bounds__(kStreamThreads) k_export_radiance(Band band, ParamsView<R> par, PathView<R> pv, double* out_rgb) {
   uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= band.n_pix) return;
-  uint32_t rw = (uint32_t)(band.x1 - band.x0);
-  uint32_t py = pix / rw;
-  size_t g = (size_t)(band.y0 + (int)py) * par.width + (band.x0 + (int)(pix - py * rw));
+  int px, py;
+  band_pix_xy(band, pix, px, py);
+  size_t g = (size_t)py * par.width + px;
   V4<R> c = ld4(&pv.radiance[pix]);
   out_rgb[g * 3 + 0] = (double)c.x;
   out_rgb[g * 3 + 1] = (double)c.y;
@@ -1687,9 +1702,9 @@ __global__ void __launch_bounds__(kStreamThreads) k_overlay_prims(SceneView<R> s
                                                                    int cur, int32_t* out) {
   uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= band.n_pix) return;
-  uint32_t rw = (uint32_t)(band.x1 - band.x0);
-  uint32_t py = pix / rw;
-  size_t g = (size_t)(band.y0 + (int)py) * par.width + (band.x0 + (int)(pix - py * rw));
+  int px, py;
+  band_pix_xy(band, pix, px, py);
+  size_t g = (size_t)py * par.width + px;
   const uint32_t code = code_of(pv.hnrm[cur][pix].w);
   out[g] = code == HIT_MISS ? -1 : sc.prim_id[code & REF_SLOT_MASK];
 }
