@@ -789,9 +789,6 @@ constexpr int kStreamThreads = 256;
 #ifndef RTC_SHADE_MIN_BLOCKS
 #define RTC_SHADE_MIN_BLOCKS 3
 #endif
-#ifndef RTC_PREFETCH
-#define RTC_PREFETCH 0
-#endif
 constexpr int kTraceThreads = RTC_TRACE_THREADS;
 constexpr int kTraceMinBlocks = RTC_TRACE_MIN_BLOCKS;
 
@@ -851,12 +848,14 @@ struct TraceIO {
 // warp-uniform loop whose every iteration runs exactly one of three bodies, chosen by warp vote:
 //   refill  lanes whose ray is finished write its Hit record and take the next queue entries (one warp-aggregated
 //           atomicAdd on a global cursor); taken when more than 32 - kRefill lanes are idle (Aila & Laine 2009);
-//   node    lanes standing on an inner node fetch it (4 x 16-byte loads), test both child boxes, descend to the
-//           nearer child and push the farther one;
+//   node    lanes standing on an inner node fetch it, test its child boxes (f64 mode: four, with the reference's own slab
+//           arithmetic), descend to the nearest hit child and push the others, farthest first;
 //   leaf    lanes standing on a leaf test its primitive and pop their next stack entry.
 // node vs leaf is greedy: whichever has more lanes ready runs, the other lanes wait. Leaves are ~1 in 16 steps of a
 // ray, so a plain while-while loop (all lanes reach a leaf before any is tested) leaves ~3/4 of the lanes idle.
 // The per-lane stack holds (node, box near) pairs so stale entries are discarded without fetching the node.
+// k_trace below is the f64 parity kernel (uncompressed 4-wide nodes); the f32 production kernel k_trace_q8 further down
+// uses the same scheduler over quantised 8-wide nodes.
 #ifndef RTC_REFILL
 #define RTC_REFILL 26
 #endif
@@ -913,7 +912,7 @@ __device__ __forceinline__ void stack_pop(const TraceStack<R>& stk, int& sp, R b
 }
 
 template <typename R, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinBlocks) k_trace(SceneView<R> sc, TraceIO<R> io) {
+__global__ void __launch_bounds__(kTraceThreads, 2) k_trace(SceneView<R> sc, TraceIO<R> io) {
   const uint32_t count = *io.count;
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -925,8 +924,7 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
   bool finished = false;    // the lane holds a finished ray whose Hit record is not written yet
   bool exhausted = false;   // warp-uniform: the queue has no more entries
   uint32_t path = 0;
-  V3<R> o = mk3(R(0), R(0), R(0)), d = o, inv = o, oinv = o;
-  uint32_t sgn = 0;
+  V3<R> o = mk3(R(0), R(0), R(0)), d = o, inv = o;
   Skip<R> sk;
   sk.code = HIT_MISS;
   SkipSrc<R> src;
@@ -971,15 +969,7 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
           const uint32_t code = code_of(io.in_hnrm[path].w);
           o = xyz(op);
           d = xyz(dv);
-          if constexpr (Num<R>::is_f64)
-            inv = mk3(R(1) / d.x, R(1) / d.y, R(1) / d.z);  // AABB.cs:129
-          else {
-            // f32: slabs are evaluated as fma(bound, inv, -o*inv) on the bounds pre-selected by the direction's sign,
-            // so a zero component must not produce inf - inf: its reciprocal is clamped to +-2^64.
-            inv = mk3(clamped_rcp(d.x), clamped_rcp(d.y), clamped_rcp(d.z));
-            oinv = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
-            sgn = (rsignbit(d.x) ? 1u : 0u) | (rsignbit(d.y) ? 2u : 0u) | (rsignbit(d.z) ? 4u : 0u);
-          }
+          inv = mk3(R(1) / d.x, R(1) / d.y, R(1) / d.z);  // AABB.cs:129
           sk.code = code;
           best.t = Num<R>::inf();
           best.near_ = 0;
@@ -1004,7 +994,7 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
         uint32_t ch[W];
         R key[W];
         int nh = 0;
-        if constexpr (Num<R>::is_f64) {
+        {
           R lo[3][W], hi[3][W];
 #pragma unroll
           for (int a = 0; a < 3; a++) {
@@ -1021,38 +1011,12 @@ __global__ void __launch_bounds__(kTraceThreads, Num<R>::is_f64 ? 2 : kTraceMinB
             key[c] = h ? nr : Num<R>::inf();
             nh += h ? 1 : 0;
           }
-        } else {
-          // near / far bound rows picked by the ray's direction signs: no per-slab min/max
-          R bn[3][W], bf[3][W];
-          load_row<R, W>((sgn & 1u) ? np->hi[0] : np->lo[0], bn[0]);
-          load_row<R, W>((sgn & 1u) ? np->lo[0] : np->hi[0], bf[0]);
-          load_row<R, W>((sgn & 2u) ? np->hi[1] : np->lo[1], bn[1]);
-          load_row<R, W>((sgn & 2u) ? np->lo[1] : np->hi[1], bf[1]);
-          load_row<R, W>((sgn & 4u) ? np->hi[2] : np->lo[2], bn[2]);
-          load_row<R, W>((sgn & 4u) ? np->lo[2] : np->hi[2], bf[2]);
-          load_children<W>(np->child, ch);
-#pragma unroll
-          for (int c = 0; c < W; c++) {
-            const R tnx = fmaf(bn[0][c], inv.x, oinv.x), tny = fmaf(bn[1][c], inv.y, oinv.y), tnz = fmaf(bn[2][c], inv.z, oinv.z);
-            const R tfx = fmaf(bf[0][c], inv.x, oinv.x), tfy = fmaf(bf[1][c], inv.y, oinv.y), tfz = fmaf(bf[2][c], inv.z, oinv.z);
-            const R nr = fmaxf(fmaxf(tnx, tny), tnz);
-            const R fr = fminf(fminf(fminf(tfx, tfy), tfz), best.t);  // far >= 0 and near <= best.t folded in
-            const bool h = (nr <= fr) && (fr >= 0.0f);               // empty children have (+inf, -inf) boxes
-            key[c] = h ? nr : Num<R>::inf();
-            nh += h ? 1 : 0;
-          }
         }
         if (COUNT) n_nodes++;
         sort_children<R, W>(key, ch);  // hits first, nearest first (misses carry +inf keys)
 #pragma unroll
         for (int c = W - 1; c >= 1; c--) {
           if (c < nh) {  // farthest pushed first, so the nearest pending child is popped first
-#if RTC_PREFETCH
-            {
-              const void* pf = (ch[c] & REF_LEAF) ? (const void*)(sc.prims + (ch[c] & REF_SLOT_MASK)) : (const void*)(sc.nodes + ch[c]);
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-            }
-#endif
             stk.push(sp, ch[c], key[c]);
             sp++;
           }
