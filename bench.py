@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--max-paths", type=int, default=0)
+    ap.add_argument("--no-other-scenes", action="store_true", help="skip the short per-scene runs of the other BASELINE configs")
+    ap.add_argument("--with-soup10m", action="store_true", help="include the 10 M-triangle scene in the per-scene runs (its BVH build takes ~10 s)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
@@ -380,6 +382,34 @@ def main():
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, sc, args.cpu_seconds)
+        if world == 1 and not args.no_other_scenes:
+            # BASELINE.json quotes the metric "per scene": short device-resident runs of the other configs (3 warm-up + 4
+            # timed steps each, CUDA events on the launching stream), reported beside the headline workload
+            others = [w for w in ("bounce", "die", "spheres100k") + (("soup10m",) if args.with_soup10m else ()) if w != args.workload]
+            per_scene = {}
+            for w in others:
+                wl2 = WORKLOADS[w]
+                sc2 = make_scene(w)
+                c2 = Context(local, prec)
+                c2.set_stream(stream.cuda_stream)
+                c2.load(sc2, seed=1)
+                for i in range(3):
+                    c2.render(i * wl2["spp"], wl2["spp"])
+                c2.sync()
+                c2.reset_stats()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                for i in range(4):
+                    c2.render((3 + i) * wl2["spp"], wl2["spp"])
+                a1.record(stream)
+                c2.sync()
+                t2 = a0.elapsed_time(a1) * 1e-3
+                st3 = c2.stats()
+                per_scene[w] = {"value": st3.rays / t2 / 1e6, "unit": "Mrays/s", "spp_mpix_per_s": st3.paths / t2 / 1e6,
+                                "ms_per_step": t2 / 4 * 1e3, "description": wl2["desc"], "spp_per_step": wl2["spp"],
+                                "n_prims": sc2.n_prims}
+                c2.close()
+            line["per_scene"] = per_scene
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
