@@ -145,6 +145,8 @@ typedef struct rtc_debug_ray {
 } rtc_debug_ray;
 
 enum {
+  /* (RTC_K_COMPACT: the stream compaction itself is fused into the shade kernel; this slot times the one-thread
+   *  bookkeeping launch between bounces) */
   RTC_K_RAYGEN = 0, RTC_K_TRACE = 1, RTC_K_SHADE = 2, RTC_K_COMPACT = 3, RTC_K_ACCUMULATE = 4, RTC_K_COUNT = 5
 };
 
