@@ -843,6 +843,24 @@ struct TraceIO {
   Control* ctl;
 };
 
+// The same for one shade launch (dynamic indexing of pointer arrays inside a kernel parameter forces a local-memory copy of
+// the whole parameter block and a local load per access).
+template <typename R>
+struct ShadeIO {
+  V4<R>* dir;             // [path] in: ray direction, out: next direction
+  V4<R>* tint;            // [path] throughput
+  const V4<R>* org;       // [path] xyz = this bounce's ray origin (the previous hit record)
+  V4<R>* hpos;            // [path] this bounce's hit: in w = Hit.Distance, out xyz = position
+  V4<R>* hnrm;            // [path] in w = hit code, out xyz = normal
+  V4<R>* radiance;        // [path] out for finished paths
+  const uint32_t* queue;  // live path ids of this bounce, or nullptr for the identity queue (bounce 0)
+  const uint32_t* count;  // their number
+  uint32_t* queue_out;    // survivors are appended here ...
+  uint32_t* count_out;    // ... and counted here
+  int32_t* dbg_type;      // optional per-path BounceType (rtc_debug_trace)
+  R* dbg_fresnel;         // optional per-path FresnelRatio
+};
+
 // trace: persistent warps, one ray per lane, scheduled warp-synchronously. On sm_70+ a per-lane `while` nest is not
 // re-converged at loop exits and degenerates into lanes issuing one at a time, so the kernel is written as ONE
 // warp-uniform loop whose every iteration runs exactly one of three bodies, chosen by warp vote:
@@ -1343,12 +1361,13 @@ __device__ __forceinline__ R luminance(R r, R g, R b) { return (R(0.299) * r + R
 // radiance; the survivors overwrite dir/tint in place and are appended to the next bounce's queue by a warp-aggregated
 // stream compaction (ballot + popc + one atomicAdd per warp) -- the loop's `break`/`return` of the reference.
 template <typename R>
-__global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(SceneView<R> sc, ParamsView<R> par, Band band, PathView<R> pv, int q,
-                                                           int cur, int bounce, int identity_queue) {
-  const uint32_t count = pv.ctl->count[q];
-  const uint32_t* queue = q ? pv.queue[1] : pv.queue[0];
-  uint32_t* qout = q ? pv.queue[0] : pv.queue[1];
-  uint32_t* out_count = &pv.ctl->count[q ^ 1];
+__global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(SceneView<R> sc, ParamsView<R> par, Band band, ShadeIO<R> io,
+                                                           int bounce) {
+  const uint32_t count = *io.count;
+  const uint32_t* queue = io.queue;
+  uint32_t* qout = io.queue_out;
+  uint32_t* out_count = io.count_out;
+  const int identity_queue = io.queue == nullptr;
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t rounds = (count + stride - 1) / stride;  // warp-uniform trip count: every lane takes part in the ballots
   uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1357,18 +1376,18 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
     uint32_t path = 0;
     if (idx < count) {
     path = identity_queue ? idx : queue[idx];
-    V4<R> hp = ld4(&pv.hpos[cur][path]);
-    V4<R> hn = ld4(&pv.hnrm[cur][path]);
+    V4<R> hp = ld4(&io.hpos[path]);
+    V4<R> hn = ld4(&io.hnrm[path]);
     const uint32_t code = code_of(hn.w);
     if (code != HIT_MISS) {  // complete the Hit record: it is also the next ray's origin and skip hit
-      V3<R> ro = xyz(ld4(&pv.hpos[cur ^ 1][path])), rd = xyz(ld4(&pv.dir[path]));
+      V3<R> ro = xyz(ld4(&io.org[path])), rd = xyz(ld4(&io.dir[path]));
       V3<R> fp, fn;
       R ft;
       finalize_hit<R>(sc, code, ro, rd, fp, fn, ft);
       hp.x = fp.x; hp.y = fp.y; hp.z = fp.z; hp.w = ft;
       hn.x = fn.x; hn.y = fn.y; hn.z = fn.z;
-      st4(&pv.hpos[cur][path], hp.x, hp.y, hp.z, hp.w);
-      st4(&pv.hnrm[cur][path], hn.x, hn.y, hn.z, hn.w);
+      st4(&io.hpos[path], hp.x, hp.y, hp.z, hp.w);
+      st4(&io.hnrm[path], hn.x, hn.y, hn.z, hn.w);
     }
     bool done = false;
     R out_r = 0, out_g = 0, out_b = 0;
@@ -1389,7 +1408,7 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
       const bool hit_inside = (code & HIT_INSIDE) != 0;
       const DMat<R>* mp = sc.mats + slot;
       V4<R> m_emis = ldg4(&mp->emis_ior), m_diff = ldg4(&mp->diff_shin), m_spec = ldg4(&mp->spec), m_refr = ldg4(&mp->refr);
-      V4<R> tv = ld4(&pv.tint[path]);
+      V4<R> tv = ld4(&io.tint[path]);
       if (par.debug_geom) {  // :93-98
         dbg = 9;
         out_r = (m_spec.x + m_diff.x) + m_emis.x;
@@ -1408,7 +1427,7 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
         band_pixel(band, path, x, y, sample);
         const uint32_t pixel = (uint32_t)(y * par.width + x);
         const uint32_t stage = 1u + (uint32_t)bounce;
-        V4<R> dv = ld4(&pv.dir[path]);
+        V4<R> dv = ld4(&io.dir[path]);
         V3<R> d = xyz(dv), normal = xyz(hn);
         const R shininess = m_diff.w, ior = m_emis.w;
         R u1, u2;
@@ -1495,8 +1514,8 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
           R m = risnan(total_l) ? total_l : (total_l > 1 ? total_l : R(1));  // Math.Max(totalLum, 1), :238
           R tr = tv.x * (nt_r * m), tg = tv.y * (nt_g * m), tb = tv.z * (nt_b * m);  // :238-240
           if ((bounce + 1) % 3 == 0) out_dir = normalize3(out_dir);  // :74-75 of the next iteration
-          st4(&pv.dir[path], out_dir.x, out_dir.y, out_dir.z, R(0));
-          st4(&pv.tint[path], tr, tg, tb, R(0));
+          st4(&io.dir[path], out_dir.x, out_dir.y, out_dir.z, R(0));
+          st4(&io.tint[path], tr, tg, tb, R(0));
         } else {
           out_r = tv.x * m_emis.x;  // :245
           out_g = tv.y * m_emis.y;
@@ -1505,12 +1524,12 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
         }
       }
     }
-    if (pv.dbg_type) {
-      pv.dbg_type[path] = dbg;
-      pv.dbg_fresnel[path] = dbg_f;
+    if (io.dbg_type) {
+      io.dbg_type[path] = dbg;
+      io.dbg_fresnel[path] = dbg_f;
     }
     if (done)
-      st4(&pv.radiance[path], out_r, out_g, out_b, R(0));
+      st4(&io.radiance[path], out_r, out_g, out_b, R(0));
     alive = !done;
     }
     const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
@@ -1757,7 +1776,20 @@ template <typename R>
 cudaError_t Kernels<R>::shade(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,
                               const PathView<R>& pv, int q, int cur, int bounce, bool identity_queue) {
   int grid = cfg.sm_count * 8;
-  k_shade<R><<<grid, kStreamThreads, 0, cfg.stream>>>(sc, par, band, pv, q, cur, bounce, identity_queue ? 1 : 0);
+  ShadeIO<R> io;
+  io.dir = pv.dir;
+  io.tint = pv.tint;
+  io.org = pv.hpos[cur ^ 1];
+  io.hpos = pv.hpos[cur];
+  io.hnrm = pv.hnrm[cur];
+  io.radiance = pv.radiance;
+  io.queue = identity_queue ? nullptr : pv.queue[q];
+  io.count = &pv.ctl->count[q];
+  io.queue_out = pv.queue[q ^ 1];
+  io.count_out = &pv.ctl->count[q ^ 1];
+  io.dbg_type = pv.dbg_type;
+  io.dbg_fresnel = pv.dbg_fresnel;
+  k_shade<R><<<grid, kStreamThreads, 0, cfg.stream>>>(sc, par, band, io, bounce);
   return cudaGetLastError();
 }
 
