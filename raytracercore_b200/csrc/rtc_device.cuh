@@ -1379,8 +1379,19 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
     V4<R> hp = ld4(&io.hpos[path]);
     V4<R> hn = ld4(&io.hnrm[path]);
     const uint32_t code = code_of(hn.w);
+    // every load that depends on (path, slot) only is issued up front, behind one another: the kernel is bound by gather
+    // latency, not by arithmetic
+    V4<R> m_emis, m_diff, m_spec, m_refr, tv, dv;
     if (code != HIT_MISS) {  // complete the Hit record: it is also the next ray's origin and skip hit
-      V3<R> ro = xyz(ld4(&io.org[path])), rd = xyz(ld4(&io.dir[path]));
+      const DMat<R>* mp = sc.mats + (code & REF_SLOT_MASK);
+      V3<R> ro = xyz(ld4(&io.org[path]));
+      dv = ld4(&io.dir[path]);
+      m_emis = ldg4(&mp->emis_ior);
+      m_diff = ldg4(&mp->diff_shin);
+      m_spec = ldg4(&mp->spec);
+      m_refr = ldg4(&mp->refr);
+      tv = ld4(&io.tint[path]);
+      V3<R> rd = xyz(dv);
       V3<R> fp, fn;
       R ft;
       finalize_hit<R>(sc, code, ro, rd, fp, fn, ft);
@@ -1404,11 +1415,8 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
       }
       done = true;
     } else {
-      const uint32_t slot = code & REF_SLOT_MASK;
       const bool hit_inside = (code & HIT_INSIDE) != 0;
-      const DMat<R>* mp = sc.mats + slot;
-      V4<R> m_emis = ldg4(&mp->emis_ior), m_diff = ldg4(&mp->diff_shin), m_spec = ldg4(&mp->spec), m_refr = ldg4(&mp->refr);
-      V4<R> tv = ld4(&io.tint[path]);
+
       if (par.debug_geom) {  // :93-98
         dbg = 9;
         out_r = (m_spec.x + m_diff.x) + m_emis.x;
@@ -1427,7 +1435,6 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
         band_pixel(band, path, x, y, sample);
         const uint32_t pixel = (uint32_t)(y * par.width + x);
         const uint32_t stage = 1u + (uint32_t)bounce;
-        V4<R> dv = ld4(&io.dir[path]);
         V3<R> d = xyz(dv), normal = xyz(hn);
         const R shininess = m_diff.w, ior = m_emis.w;
         R u1, u2;
