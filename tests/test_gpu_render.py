@@ -344,6 +344,33 @@ def test_render_read_equals_render_then_read():
         ctx.close()
 
 
+def test_repeated_staged_uploads_and_frames():
+    """The end-to-end frame loop of bench.py: re-upload the pinned scene image (its shading half arrives on the copy stream
+    behind the first trace launch), clear, render + read back -- five times, alternating two different scenes in the same
+    context, each frame bit-identical to a fresh context's."""
+    scenes = [cornell(64, 48, 6), die(64, 48, 3)]
+    want, baked = [], []
+    for sc in scenes:
+        c = Context(0, RTC_F32)
+        c.load(sc, seed=4)
+        c.render(0, 3)
+        want.append(c.read_accum())
+        baked.append(c.bake())
+        c.close()
+    ctx = Context(0, RTC_F32)
+    for i in range(5):
+        k = i & 1
+        ctx.upload_baked(baked[k])
+        ctx.set_params(scenes[k].params(4))
+        ctx.set_camera(scenes[k].camera())
+        ctx.clear_accum()
+        got = ctx.render_read(0, 3)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want[k])), (i, k)
+    ctx.close()
+    for b in baked:
+        b.close()
+
+
 def test_baked_scene_image_round_trip():
     """rtc_bake / rtc_upload_baked: the host-resident device image renders exactly like the original hand-over."""
     sc = cornell(64, 64, 6)
