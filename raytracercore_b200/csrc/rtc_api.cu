@@ -425,6 +425,29 @@ int upload_baked_image(rtc_ctx* ctx, const rtc_baked* bk) {
 }
 
 // Flatten the reference-shaped tree + primitives into the device layout (see rtc_internal.h).
+// Chunked parallel loop over [begin, end) on the host's threads (serial below `grain` items per thread).
+template <typename F>
+void parallel_for(size_t begin, size_t end, size_t grain, F&& fn) {
+  const size_t n = end > begin ? end - begin : 0;
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = std::min<size_t>(hw ? std::min(hw, 16u) : 1, n / std::max<size_t>(grain, 1));
+  if (nt <= 1) {
+    for (size_t i = begin; i < end; i++) fn(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  const size_t per = (n + nt - 1) / nt;
+  for (size_t t = 0; t < nt; t++) {
+    const size_t b = begin + t * per, e = std::min(end, b + per);
+    if (b >= e) break;
+    th.emplace_back([b, e, &fn]() {
+      for (size_t i = b; i < e; i++) fn(i);
+    });
+  }
+  for (auto& t : th) t.join();
+}
+
 // RTC_B200_VERBOSE: wall-clock of the phases of build_device_scene
 struct PhaseTimer {
   bool on = std::getenv("RTC_B200_VERBOSE") != nullptr;
@@ -721,120 +744,147 @@ int build_device_scene(rtc_ctx* ctx) {
       queue.reserve((size_t)n_bounded / 3 + 16);
       queue.push_back({resolve(ctx->root), 1});
       qn.reserve((size_t)n_bounded / 3 + 16);
-      for (size_t qi = 0; qi < queue.size(); qi++) {
-        const QWork wk = queue[qi];
-        max_depth = std::max(max_depth, wk.depth);
+      // Level by level. Phase A (parallel over the level's nodes): children, box, grid, slot assignment, quantised bounds --
+      // everything but the two base indices. Phase B (serial, cheap): child_base / prim_base in emission order, leaf slots,
+      // and the next level's queue entries, children in slot order exactly as a serial breadth-first pass would push them.
+      struct Emit {
         int32_t kids[8];
-        int nk = 0;
-        if (nodes[wk.bnode].prim >= 0) {
-          kids[nk++] = wk.bnode;  // tree of a single bounded primitive
-        } else {
-          gather_children(wk.bnode, kids, nk);
-        }
-        // node box, grid origin and per-axis power-of-two step
-        double lo[3], hi[3];
-        for (int a = 0; a < 3; a++) {
-          lo[a] = std::numeric_limits<double>::infinity();
-          hi[a] = -std::numeric_limits<double>::infinity();
-          for (int c = 0; c < nk; c++) {
-            lo[a] = std::min(lo[a], fmin[(size_t)kids[c] * 3 + a]);
-            hi[a] = std::max(hi[a], fmax[(size_t)kids[c] * 3 + a]);
-          }
-        }
+        int8_t child_in_slot[8];
+        int nk;
         CNode cn;
-        std::memset(&cn, 0, sizeof(cn));
-        float p[3];
-        int ex[3];
-        double step[3];
-        for (int a = 0; a < 3; a++) {
-          // grid: origin one step below the box minimum (so the one-step padding of the children never clamps at 0),
-          // step = smallest power of two that spans the box in 250 steps
-          double ext = hi[a] - lo[a];
-          int e = ext > 0 ? (int)std::ceil(std::log2(ext / 250.0)) : -100;
-          e = std::min(std::max(e, -120), 120);
-          while (std::ldexp(1.0, e) * 250.0 < ext) e++;
-          p[a] = round_down<float>(lo[a] - std::ldexp(1.0, e));
-          while (std::ldexp(1.0, e) * 253.0 < hi[a] - (double)p[a]) {
-            e++;
-            p[a] = round_down<float>(lo[a] - std::ldexp(1.0, e));
-          }
-          ex[a] = e;
-          step[a] = std::ldexp(1.0, e);
-        }
-        cn.px = p[0];
-        cn.py = p[1];
-        cn.pz = p[2];
-        // slot assignment: child i goes to the free slot whose octant signs best match its offset from the centre
-        int slot_of[8];
-        {
-          double ctr[3];
-          for (int a = 0; a < 3; a++) ctr[a] = 0.5 * (lo[a] + hi[a]);
-          double cost[8][8];
-          for (int c = 0; c < nk; c++)
-            for (int s2 = 0; s2 < 8; s2++) {
-              double v = 0;
-              for (int a = 0; a < 3; a++) {
-                double off = 0.5 * (fmin[(size_t)kids[c] * 3 + a] + fmax[(size_t)kids[c] * 3 + a]) - ctr[a];
-                v += ((s2 >> a) & 1) ? off : -off;
-              }
-              cost[c][s2] = v;
-            }
-          bool cu[8] = {false, false, false, false, false, false, false, false}, su[8] = {false, false, false, false, false, false, false, false};
-          for (int it = 0; it < nk; it++) {
-            int bc = -1, bs = -1;
-            double bv = -std::numeric_limits<double>::infinity();
-            for (int c = 0; c < nk; c++)
-              if (!cu[c])
-                for (int s2 = 0; s2 < 8; s2++)
-                  if (!su[s2] && cost[c][s2] > bv) {
-                    bv = cost[c][s2];
-                    bc = c;
-                    bs = s2;
-                  }
-            cu[bc] = true;
-            su[bs] = true;
-            slot_of[bc] = bs;
-          }
-        }
-        int child_in_slot[8];
-        for (int s2 = 0; s2 < 8; s2++) child_in_slot[s2] = -1;
-        for (int c = 0; c < nk; c++) child_in_slot[slot_of[c]] = c;
-        uint32_t imask = 0, lmask = 0;
-        cn.child_base = (uint32_t)queue.size();
-        cn.prim_base = (uint32_t)next_slot;
-        uint8_t qb[6][8];
-        std::memset(qb, 0, sizeof(qb));
-        for (int s2 = 0; s2 < 8; s2++) {
-          int c = child_in_slot[s2];
-          if (c < 0) {
-            for (int a = 0; a < 3; a++) {  // empty slot: inverted box, never hit
-              qb[a][s2] = 255;
-              qb[3 + a][s2] = 0;
-            }
-            continue;
-          }
-          int32_t k = kids[c];
-          for (int a = 0; a < 3; a++) {
-            double ql = std::floor((fmin[(size_t)k * 3 + a] - (double)p[a]) / step[a]) - 1.0;
-            double qh = std::ceil((fmax[(size_t)k * 3 + a] - (double)p[a]) / step[a]) + 1.0;
-            qb[a][s2] = (uint8_t)std::min(255.0, std::max(0.0, ql));
-            qb[3 + a][s2] = (uint8_t)std::min(255.0, std::max(0.0, qh));
-          }
-          if (nodes[k].prim >= 0) {
-            lmask |= 1u << s2;
-            leaf_slot[k] = next_slot;
-            slot_prim[next_slot] = nodes[k].prim;
-            next_slot++;
+      };
+      std::vector<Emit> level;
+      for (size_t lv_begin = 0; lv_begin < queue.size();) {
+        const size_t lv_end = queue.size();
+        level.resize(lv_end - lv_begin);
+        parallel_for(lv_begin, lv_end, 2048, [&](size_t qi) {
+          const QWork wk = queue[qi];
+          Emit& em = level[qi - lv_begin];
+          int32_t* kids = em.kids;
+          int nk = 0;
+          if (nodes[wk.bnode].prim >= 0) {
+            kids[nk++] = wk.bnode;  // tree of a single bounded primitive
           } else {
-            imask |= 1u << s2;
-            queue.push_back({k, wk.depth + 1});
+            gather_children(wk.bnode, kids, nk);
           }
+          em.nk = nk;
+          // node box, grid origin and per-axis power-of-two step
+          double lo[3], hi[3];
+          for (int a = 0; a < 3; a++) {
+            lo[a] = std::numeric_limits<double>::infinity();
+            hi[a] = -std::numeric_limits<double>::infinity();
+            for (int c = 0; c < nk; c++) {
+              lo[a] = std::min(lo[a], fmin[(size_t)kids[c] * 3 + a]);
+              hi[a] = std::max(hi[a], fmax[(size_t)kids[c] * 3 + a]);
+            }
+          }
+          CNode& cn = em.cn;
+          std::memset(&cn, 0, sizeof(cn));
+          float p[3];
+          int ex[3];
+          double step[3];
+          for (int a = 0; a < 3; a++) {
+            // grid: origin one step below the box minimum (so the one-step padding of the children never clamps at 0),
+            // step = smallest power of two that spans the box in 250 steps
+            double ext = hi[a] - lo[a];
+            int e = ext > 0 ? (int)std::ceil(std::log2(ext / 250.0)) : -100;
+            e = std::min(std::max(e, -120), 120);
+            while (std::ldexp(1.0, e) * 250.0 < ext) e++;
+            p[a] = round_down<float>(lo[a] - std::ldexp(1.0, e));
+            while (std::ldexp(1.0, e) * 253.0 < hi[a] - (double)p[a]) {
+              e++;
+              p[a] = round_down<float>(lo[a] - std::ldexp(1.0, e));
+            }
+            ex[a] = e;
+            step[a] = std::ldexp(1.0, e);
+          }
+          cn.px = p[0];
+          cn.py = p[1];
+          cn.pz = p[2];
+          // slot assignment: child i goes to the free slot whose octant signs best match its offset from the centre
+          int slot_of[8];
+          {
+            double ctr[3];
+            for (int a = 0; a < 3; a++) ctr[a] = 0.5 * (lo[a] + hi[a]);
+            double cost[8][8];
+            for (int c = 0; c < nk; c++)
+              for (int s2 = 0; s2 < 8; s2++) {
+                double v = 0;
+                for (int a = 0; a < 3; a++) {
+                  double off = 0.5 * (fmin[(size_t)kids[c] * 3 + a] + fmax[(size_t)kids[c] * 3 + a]) - ctr[a];
+                  v += ((s2 >> a) & 1) ? off : -off;
+                }
+                cost[c][s2] = v;
+              }
+            bool cu[8] = {false, false, false, false, false, false, false, false}, su[8] = {false, false, false, false, false, false, false, false};
+            for (int it = 0; it < nk; it++) {
+              int bc = -1, bs = -1;
+              double bv = -std::numeric_limits<double>::infinity();
+              for (int c = 0; c < nk; c++)
+                if (!cu[c])
+                  for (int s2 = 0; s2 < 8; s2++)
+                    if (!su[s2] && cost[c][s2] > bv) {
+                      bv = cost[c][s2];
+                      bc = c;
+                      bs = s2;
+                    }
+              cu[bc] = true;
+              su[bs] = true;
+              slot_of[bc] = bs;
+            }
+          }
+          for (int s2 = 0; s2 < 8; s2++) em.child_in_slot[s2] = -1;
+          for (int c = 0; c < nk; c++) em.child_in_slot[slot_of[c]] = (int8_t)c;
+          uint32_t imask = 0, lmask = 0;
+          uint8_t qb[6][8];
+          std::memset(qb, 0, sizeof(qb));
+          for (int s2 = 0; s2 < 8; s2++) {
+            int c = em.child_in_slot[s2];
+            if (c < 0) {
+              for (int a = 0; a < 3; a++) {  // empty slot: inverted box, never hit
+                qb[a][s2] = 255;
+                qb[3 + a][s2] = 0;
+              }
+              continue;
+            }
+            int32_t k = kids[c];
+            for (int a = 0; a < 3; a++) {
+              double ql = std::floor((fmin[(size_t)k * 3 + a] - (double)p[a]) / step[a]) - 1.0;
+              double qh = std::ceil((fmax[(size_t)k * 3 + a] - (double)p[a]) / step[a]) + 1.0;
+              qb[a][s2] = (uint8_t)std::min(255.0, std::max(0.0, ql));
+              qb[3 + a][s2] = (uint8_t)std::min(255.0, std::max(0.0, qh));
+            }
+            if (nodes[k].prim >= 0)
+              lmask |= 1u << s2;
+            else
+              imask |= 1u << s2;
+          }
+          cn.e_imask = (uint32_t)(ex[0] + 127) | ((uint32_t)(ex[1] + 127) << 8) | ((uint32_t)(ex[2] + 127) << 16) | (imask << 24);
+          cn.lmask = lmask;
+          for (int r = 0; r < 6; r++)
+            for (int s2 = 0; s2 < 8; s2++) cn.q[r * 2 + (s2 >> 2)] |= (uint32_t)qb[r][s2] << (8 * (s2 & 3));
+        });
+        for (size_t qi = lv_begin; qi < lv_end; qi++) {
+          const int32_t depth = queue[qi].depth;
+          max_depth = std::max(max_depth, depth);
+          Emit& em = level[qi - lv_begin];
+          em.cn.child_base = (uint32_t)queue.size();
+          em.cn.prim_base = (uint32_t)next_slot;
+          for (int s2 = 0; s2 < 8; s2++) {
+            const int c = em.child_in_slot[s2];
+            if (c < 0) continue;
+            const int32_t k = em.kids[c];
+            if (nodes[k].prim >= 0) {
+              leaf_slot[k] = next_slot;
+              slot_prim[next_slot] = nodes[k].prim;
+              next_slot++;
+            } else {
+              queue.push_back({k, depth + 1});
+            }
+          }
+          qn.push_back(em.cn);
         }
-        cn.e_imask = (uint32_t)(ex[0] + 127) | ((uint32_t)(ex[1] + 127) << 8) | ((uint32_t)(ex[2] + 127) << 16) | (imask << 24);
-        cn.lmask = lmask;
-        for (int r = 0; r < 6; r++)
-          for (int s2 = 0; s2 < 8; s2++) cn.q[r * 2 + (s2 >> 2)] |= (uint32_t)qb[r][s2] << (8 * (s2 & 3));
-        qn.push_back(cn);
+        lv_begin = lv_end;
       }
     }
     if (std::getenv("RTC_B200_VERBOSE")) {
@@ -872,7 +922,8 @@ int build_device_scene(rtc_ctx* ctx) {
     prim_ref[leaf_slot[i]] = leaf_ref(i);
   }
   (void)node_seen;
-  for (int32_t s = 0; s < n; s++) {
+  parallel_for(0, (size_t)n, 65536, [&](size_t si) {  // (every slot writes its own records; id_to_slot[p] is a permutation)
+    const int32_t s = (int32_t)si;
     int32_t p = slot_prim[s];
     prim_id[s] = p;
     id_to_slot[p] = s;
@@ -898,7 +949,7 @@ int build_device_scene(rtc_ctx* ctx) {
     dmat.diff_shin = V4<R>{(R)m[3], (R)m[4], (R)m[5], (R)m[13]};
     dmat.spec = reflective ? V4<R>{(R)m[6], (R)m[7], (R)m[8], R(0)} : V4<R>{R(0), R(0), R(0), R(0)};
     dmat.refr = reflective ? V4<R>{(R)m[9], (R)m[10], (R)m[11], R(0)} : V4<R>{R(0), R(0), R(0), R(0)};
-  }
+  });
   std::vector<DXform<R>> dx(std::max(1, ctx->n_xforms));
   std::memset(dx.data(), 0, dx.size() * sizeof(DXform<R>));
   for (int32_t j = 0; j < ctx->n_xforms; j++) {
