@@ -448,6 +448,47 @@ void parallel_for(size_t begin, size_t end, size_t grain, F&& fn) {
   for (auto& t : th) t.join();
 }
 
+// Calls post(i) for every node of the binary tree below `root`, children before their parent. The subtrees hanging off the
+// top levels run on the host threads (post(i) may only write what belongs to node i and read what belongs to descendants).
+template <typename F>
+void postorder_parallel(const std::vector<rtc_bvh_node>& nodes, int32_t root, F&& post) {
+  std::vector<int32_t> top, frontier{root};
+  while (frontier.size() < 128 && top.size() < 4096) {
+    std::vector<int32_t> next;
+    bool any = false;
+    for (int32_t i : frontier) {
+      if (nodes[i].prim < 0) {
+        top.push_back(i);
+        next.push_back(nodes[i].left);
+        next.push_back(nodes[i].right);
+        any = true;
+      } else {
+        post(i);  // a leaf this high up: done right away
+      }
+    }
+    frontier.swap(next);
+    if (!any) break;
+  }
+  parallel_for(0, frontier.size(), 1, [&](size_t f) {
+    std::vector<std::pair<int32_t, int>> st;
+    st.push_back({frontier[f], 0});
+    while (!st.empty()) {
+      auto& t = st.back();
+      const int32_t i = t.first;
+      const rtc_bvh_node& nd = nodes[i];
+      if (nd.prim < 0 && t.second == 0) {
+        t.second = 1;
+        st.push_back({nd.right, 0});
+        st.push_back({nd.left, 0});
+      } else {
+        st.pop_back();
+        post(i);
+      }
+    }
+  });
+  for (size_t k = top.size(); k-- > 0;) post(top[k]);  // (breadth-first order reversed: children first)
+}
+
 // RTC_B200_VERBOSE: wall-clock of the phases of build_device_scene
 struct PhaseTimer {
   bool on = std::getenv("RTC_B200_VERBOSE") != nullptr;
@@ -613,38 +654,26 @@ int build_device_scene(rtc_ctx* ctx) {
     // fbox = union of the finite leaf boxes below a binary node, nf = their number (post-order over the tree)
     std::vector<double> fmin((size_t)nn * 3, std::numeric_limits<double>::infinity()), fmax((size_t)nn * 3, -std::numeric_limits<double>::infinity());
     std::vector<int32_t> nf(nn, 0);
-    {
-      std::vector<std::pair<int32_t, int>> st;
-      st.push_back({ctx->root, 0});
-      while (!st.empty()) {
-        auto& top = st.back();
-        int32_t i = top.first;
-        const rtc_bvh_node& nd = nodes[i];
-        if (nd.prim >= 0) {
-          bool fin = true;
-          for (int a = 0; a < 3; a++) fin = fin && std::isfinite(nd.bmin[a]) && std::isfinite(nd.bmax[a]);
-          if (fin) {
-            nf[i] = 1;
-            for (int a = 0; a < 3; a++) {
-              fmin[(size_t)i * 3 + a] = nd.bmin[a];
-              fmax[(size_t)i * 3 + a] = nd.bmax[a];
-            }
-          }
-          st.pop_back();
-        } else if (top.second == 0) {
-          top.second = 1;
-          st.push_back({nd.right, 0});
-          st.push_back({nd.left, 0});
-        } else {
-          nf[i] = nf[nd.left] + nf[nd.right];
+    postorder_parallel(nodes, ctx->root, [&](int32_t i) {
+      const rtc_bvh_node& nd = nodes[i];
+      if (nd.prim >= 0) {
+        bool fin = true;
+        for (int a = 0; a < 3; a++) fin = fin && std::isfinite(nd.bmin[a]) && std::isfinite(nd.bmax[a]);
+        if (fin) {
+          nf[i] = 1;
           for (int a = 0; a < 3; a++) {
-            fmin[(size_t)i * 3 + a] = std::min(fmin[(size_t)nd.left * 3 + a], fmin[(size_t)nd.right * 3 + a]);
-            fmax[(size_t)i * 3 + a] = std::max(fmax[(size_t)nd.left * 3 + a], fmax[(size_t)nd.right * 3 + a]);
+            fmin[(size_t)i * 3 + a] = nd.bmin[a];
+            fmax[(size_t)i * 3 + a] = nd.bmax[a];
           }
-          st.pop_back();
+        }
+      } else {
+        nf[i] = nf[nd.left] + nf[nd.right];
+        for (int a = 0; a < 3; a++) {
+          fmin[(size_t)i * 3 + a] = std::min(fmin[(size_t)nd.left * 3 + a], fmin[(size_t)nd.right * 3 + a]);
+          fmax[(size_t)i * 3 + a] = std::max(fmax[(size_t)nd.left * 3 + a], fmax[(size_t)nd.right * 3 + a]);
         }
       }
-    }
+    });
     // a binary node with bounded leaves on one side only is transparent
     auto resolve = [&](int32_t i) -> int32_t {
       while (nodes[i].prim < 0) {
@@ -662,48 +691,32 @@ int build_device_scene(rtc_ctx* ctx) {
     // its slots on to its two sides. Evaluated children-first; cut[m][j] is the left side's share when j slots are split.
     std::vector<float> T((size_t)nn * 8, 0.0f);
     std::vector<uint8_t> cut((size_t)nn * 9, 0);
-    {
-      std::vector<std::pair<int32_t, int>> st;
-      st.push_back({ctx->root, 0});
-      while (!st.empty()) {
-        auto& top = st.back();
-        const int32_t i = top.first;
-        const rtc_bvh_node& nd = nodes[i];
-        if (nd.prim >= 0 || nf[i] == 0) {
-          st.pop_back();
-          continue;
-        }
-        if (top.second == 0) {
-          top.second = 1;
-          st.push_back({nd.right, 0});
-          st.push_back({nd.left, 0});
-          continue;
-        }
-        st.pop_back();
-        if (nf[nd.left] == 0 || nf[nd.right] == 0) continue;  // transparent: resolve() skips it
-        const int32_t l = resolve(nd.left), r = resolve(nd.right);
-        const float* Tl = &T[(size_t)l * 8];
-        const float* Tr = &T[(size_t)r * 8];
-        float D[9];
-        for (int j = 2; j <= 8; j++) {
-          float bestv = std::numeric_limits<float>::infinity();
-          int bestk = 1;
-          for (int k = 1; k < j; k++) {
-            const float v = Tl[std::min(k, 7)] + Tr[std::min(j - k, 7)];
-            if (v < bestv) {
-              bestv = v;
-              bestk = k;
-            }
+    postorder_parallel(nodes, ctx->root, [&](int32_t i) {
+      const rtc_bvh_node& nd = nodes[i];
+      if (nd.prim >= 0 || nf[i] == 0) return;
+      if (nf[nd.left] == 0 || nf[nd.right] == 0) return;  // transparent: resolve() skips it
+      const int32_t l = resolve(nd.left), r = resolve(nd.right);
+      const float* Tl = &T[(size_t)l * 8];
+      const float* Tr = &T[(size_t)r * 8];
+      float D[9];
+      for (int j = 2; j <= 8; j++) {
+        float bestv = std::numeric_limits<float>::infinity();
+        int bestk = 1;
+        for (int k = 1; k < j; k++) {
+          const float v = Tl[std::min(k, 7)] + Tr[std::min(j - k, 7)];
+          if (v < bestv) {
+            bestv = v;
+            bestk = k;
           }
-          D[j] = bestv;
-          cut[(size_t)i * 9 + j] = (uint8_t)bestk;
         }
-        float* Ti = &T[(size_t)i * 8];
-        const float as_node = (float)area(&fmin[(size_t)i * 3], &fmax[(size_t)i * 3]) + D[8];
-        Ti[1] = as_node;
-        for (int j = 2; j <= 7; j++) Ti[j] = std::min(as_node, D[j]);
+        D[j] = bestv;
+        cut[(size_t)i * 9 + j] = (uint8_t)bestk;
       }
-    }
+      float* Ti = &T[(size_t)i * 8];
+      const float as_node = (float)area(&fmin[(size_t)i * 3], &fmax[(size_t)i * 3]) + D[8];
+      Ti[1] = as_node;
+      for (int j = 2; j <= 7; j++) Ti[j] = std::min(as_node, D[j]);
+    });
     // fills kids[] with the children of the wide node rooted at binary node m
     auto gather_children = [&](int32_t m, int32_t* kids, int& nk) {
       struct It {
@@ -993,8 +1006,19 @@ int build_device_scene(rtc_ctx* ctx) {
     delete bk;
     return fail(ctx, RTC_ERR_NOMEM, "host allocation for the baked scene failed");
   }
-  for (int i = 0; i < rtc_baked::S_COUNT; i++)
-    if (sz[i]) std::memcpy(bk->host + bk->off[i], src[i], sz[i]);
+  {  // copy into the pinned image in 4 MB pieces on the host threads
+    struct Piece {
+      char* dst;
+      const char* src;
+      size_t len;
+    };
+    std::vector<Piece> pieces;
+    const size_t kPiece = (size_t)4 << 20;
+    for (int i = 0; i < rtc_baked::S_COUNT; i++)
+      for (size_t o = 0; o < sz[i]; o += kPiece)
+        pieces.push_back({(char*)bk->host + bk->off[i] + o, (const char*)src[i] + o, std::min(kPiece, sz[i] - o)});
+    parallel_for(0, pieces.size(), 4, [&](size_t k) { std::memcpy(pieces[k].dst, pieces[k].src, pieces[k].len); });
+  }
   delete ctx->baked;
   ctx->baked = bk;
   pt.mark("pinned image");
