@@ -75,18 +75,19 @@ def test_oracle_reproduces_the_reference_screenshots(key, spp, tile, alpha_mae, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["f32", "f64"])
 @pytest.mark.parametrize("key,spp,rgb_rel,median_band,spread", [
     ("bounce", 384, 0.02, (0.975, 1.015), (0.96, 1.03)),
     ("die", 768, 0.05, (0.95, 1.03), (0.60, 1.06)),  # (die.png itself is noisy around the two small lights)
 ])
-def test_cuda_path_reproduces_the_reference_screenshots(key, spp, rgb_rel, median_band, spread):
-    from raytracercore_b200 import RTC_F32, Context
+def test_cuda_path_reproduces_the_reference_screenshots(key, spp, rgb_rel, median_band, spread, precision):
+    from raytracercore_b200 import RTC_F32, RTC_F64, Context
     fname, rec, exposure = SHOTS[key]
     ref_a, ref_rgb = G[key + "_alpha"], G[key + "_rgb"]
     h, w = ref_a.shape[0] * BLOCK, ref_a.shape[1] * BLOCK
     sc = Scene.from_file(os.path.join(SCENES, fname))
     sc.override(width=w, height=h, recursion=rec, camera=0)
-    ctx = Context(0, RTC_F32)
+    ctx = Context(0, RTC_F32 if precision == "f32" else RTC_F64)
     ctx.load(sc, seed=1)
     ctx.render(0, spp)
     a, pre = split(ctx.tonemap(exposure, (0, 0, 0), 0.0))
