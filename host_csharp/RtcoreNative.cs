@@ -62,6 +62,16 @@ namespace RaytracerCore.Raytracing.Gpu
 	[StructLayout(LayoutKind.Sequential)]
 	public struct RtcDebugRay { public RtcHit Hit; public int Type, Pad; public double FresnelRatio; }
 
+	/// <summary>rtc_stats: RTC_K_COUNT = 5 kernel families (raygen, trace, shade, compact, accumulate).</summary>
+	[StructLayout(LayoutKind.Sequential)]
+	public unsafe struct RtcStats
+	{
+		public ulong Paths, Rays;
+		public fixed ulong Launches[5];
+		public fixed double Ms[5];
+		public ulong NodesVisited, PrimsTested, NodeSteps, LeafSteps;
+	}
+
 	public static unsafe class RtcoreNative
 	{
 		const string Lib = "rtcore_b200";   // librtcore_b200.so / rtcore_b200.dll
@@ -69,6 +79,8 @@ namespace RaytracerCore.Raytracing.Gpu
 		public const int F32 = 0, F64 = 1;
 		public const int KindTriangle = 0, KindSphere = 1, KindPlane = 2;
 		public const int FlagMirror = 1, FlagTwoSided = 2, FlagInvert = 4, FlagTransformed = 8, FlagVNormals = 16;
+		public const int OverlayPrimitives = 0, OverlayBoundingVolumes = 1;
+		public const int OptKernelTiming = 1, OptCounters = 2, OptMaxPaths = 3;
 
 		[DllImport(Lib)] public static extern int rtc_abi_version();
 		[DllImport(Lib)] public static extern int rtc_device_count();
@@ -98,10 +110,13 @@ namespace RaytracerCore.Raytracing.Gpu
 		[DllImport(Lib)] public static extern int rtc_read_accum(IntPtr ctx, double* rgbSum, uint* samples, uint* misses);
 		[DllImport(Lib)] public static extern int rtc_write_accum(IntPtr ctx, double* rgbSum, uint* samples, uint* misses);
 		[DllImport(Lib)] public static extern int rtc_accum_device_ptrs(IntPtr ctx, out IntPtr rgbSum, out IntPtr samples, out IntPtr misses);
-		[DllImport(Lib)] public static extern int rtc_tonemap_argb(IntPtr ctx, double exposure, double* backRgb, double backA, int* argb);
+		[DllImport(Lib)] public static extern int rtc_read_pixel(IntPtr ctx, int x, int y, double* rgbSum, out uint samples, out uint misses);
+		[DllImport(Lib)] public static extern int rtc_tonemap_argb(IntPtr ctx, double exposure, double* backRgb, double backA, uint* argb);
 		[DllImport(Lib)] public static extern int rtc_debug_trace(IntPtr ctx, int x, int y, uint sample, int capacity, RtcDebugRay* rays, out int n);
 		[DllImport(Lib)] public static extern int rtc_debug_raycast(IntPtr ctx, int mode, int* ids);
 		[DllImport(Lib)] public static extern int rtc_render_samples(IntPtr ctx, uint sample, double* rgb);
+		[DllImport(Lib)] public static extern int rtc_get_stats(IntPtr ctx, RtcStats* stats);
+		[DllImport(Lib)] public static extern int rtc_reset_stats(IntPtr ctx);
 		[DllImport(Lib)] public static extern int rtc_comm_unique_id(byte* id128);
 		[DllImport(Lib)] public static extern int rtc_comm_init(IntPtr ctx, int nRanks, int rank, byte* id128);
 		[DllImport(Lib)] public static extern int rtc_reduce_accum(IntPtr ctx, int root);

@@ -164,8 +164,7 @@ typedef struct rtc_stats {
 enum {
   RTC_OPT_KERNEL_TIMING = 1, /* record CUDA events around every launch (rtc_stats.ms)                  */
   RTC_OPT_COUNTERS = 2,      /* instrumented traversal (nodes_visited / prims_tested)                  */
-  RTC_OPT_MAX_PATHS = 3,     /* size of the path pool (paths in flight per wavefront)                   */
-  RTC_OPT_SORT_RAYS = 4      /* reserved                                                                */
+  RTC_OPT_MAX_PATHS = 3      /* size of the path pool (paths in flight per wavefront)                   */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------------- */
@@ -238,8 +237,15 @@ int rtc_write_accum(rtc_ctx* ctx, const double* rgb_sum, const uint32_t* samples
 /* Device addresses of the accumulation planes (rgb_sum: w*h*3 f64, samples / misses: w*h u32), for the
  * per-frame collective. */
 int rtc_accum_device_ptrs(rtc_ctx* ctx, void** rgb_sum, void** samples, void** misses);
-/* FullRaytracer.GetBitmap / SampleSet.GetOutput (FullRaytracer.cs:179-205, SampleSet.cs:61-113): ARGB8. */
+/* FullRaytracer.GetBitmap / SampleSet.GetOutput (FullRaytracer.cs:179-205, SampleSet.cs:61-113): ARGB8 of the planes as of the
+ * last accumulation issued. Converted on the device into a persistent buffer and copied out through pinned staging on a
+ * stream of its own: the render stream is not synchronised, so the UI's 100 ms refresh (FullRaytracer.cs:33,369) does not
+ * stall rendering. This call and rtc_read_pixel are the two that may be made from a second host thread while another thread
+ * is inside rtc_render / rtc_render_read / rtc_sync on the same handle. */
 int rtc_tonemap_argb(rtc_ctx* ctx, double exposure, const double back_rgb[3], double back_a, uint32_t* argb);
+/* FullRaytracer.GetSampleSet(x, y) (FullRaytracer.cs:131-146): Color sum, Samples, Misses of one pixel (MainWindow.cs:360-370
+ * calls it on every mouse move). Same threading rule as rtc_tonemap_argb. */
+int rtc_read_pixel(rtc_ctx* ctx, int32_t x, int32_t y, double rgb_sum[3], uint32_t* samples, uint32_t* misses);
 
 /* ---- inspection ------------------------------------------------------------------------------------ */
 /* Raytracer.GetDebugTrace(x, y) (Raytracer.cs:254-260,289-292) for one (pixel, sample); *n <= recursion+1. */
@@ -262,7 +268,15 @@ int rtc_reset_stats(rtc_ctx* ctx);
 #define RTC_NCCL_ID_BYTES 128
 int rtc_comm_unique_id(void* id128);
 int rtc_comm_init(rtc_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
-/* Sum rgb_sum / samples / misses of all ranks into `root` (ncclReduce over NVLink), root < 0: all-reduce. */
+/* The per-frame collective (ncclReduce / ncclAllReduce over NVLink). A rank's planes hold what it has rendered and not yet
+ * handed over; the call moves every rank's contribution into the job's running total:
+ *   root >= 0  root's planes += all other ranks' planes, which are then reset to zero on the stream. The progressive loop
+ *              `rtc_render; rtc_reduce_accum(0)` therefore accumulates on the root exactly like the single-GPU path (no
+ *              clear between frames; rtc_read_accum / rtc_tonemap_argb are meaningful on the root only).
+ *   root <  0  all-reduce: every rank ends with the running total. The library keeps a device copy of it and takes it out
+ *              again on ranks != 0 before the next collective, so the total is never contributed twice.
+ * rtc_clear_accum / rtc_write_accum / a size change start a fresh contribution on the calling rank. Collective: all ranks
+ * of the communicator must call it with the same root. */
 int rtc_reduce_accum(rtc_ctx* ctx, int32_t root);
 int rtc_comm_destroy(rtc_ctx* ctx);
 

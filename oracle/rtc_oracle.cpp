@@ -520,9 +520,16 @@ Ray get_camera_ray(const orc_scene& s, int x, int y, uint32_t sample) {  // Rayt
 // ------------------------------------------------------------------------------------------------------
 inline double luminance(const double c[3]) { return 0.299 * c[0] + 0.587 * c[1] + 0.114 * c[2]; }  // DoubleColor.cs:76-81
 
+struct RaySeg {  // one Scene.RayTrace call of a path, as GetColor made it (Raytracer.cs:77): ray, skip hit, answer, bounce
+  Ray ray;
+  Hit skip, hit;
+  int bounce;
+};
+
 struct PathCtx {
   std::vector<BI> list;
   uint64_t rays = 0;
+  std::vector<RaySeg>* dump = nullptr;  // orc_dump_path_rays: every segment is recorded here
 };
 
 enum BounceType { Skipped, Diffuse, Specular, SpecularFail, Transmitted, Emission, PureBlack, RecursionComplete, Missed, Debug };
@@ -538,6 +545,7 @@ void get_color(const orc_scene& s, Ray ray, uint32_t pixel, uint32_t sample, Pat
     if (i % 3 == 0) ray = Ray{ray.o, normalize(ray.d)};  // :74-75
     hit = scene_ray_trace_bvh(s, ray, prev_hit, ctx.list);  // :77
     ctx.rays++;
+    if (ctx.dump) ctx.dump->push_back(RaySeg{ray, prev_hit, hit, i});
     rtc_debug_ray* dr = nullptr;
     if (debug && i < debug_cap) {
       dr = &debug[i];
@@ -863,6 +871,36 @@ void orc_debug_trace(orc_scene* s, int32_t x, int32_t y, uint32_t sample, int32_
   int cnt = 0;
   get_color(*s, r, (uint32_t)(y * s->par.width + x), sample, ctx, c, out, capacity, &cnt);
   *n = cnt;
+}
+
+int64_t orc_dump_path_rays(orc_scene* s, int64_t n, const int32_t* xy, const uint32_t* sample, int threads, int64_t capacity,
+                           rtc_ray* rays, rtc_hit* skip, rtc_hit* hits, int32_t* bounce) {
+  // paths are traced in parallel, their segments stored in path order (deterministic for any thread count)
+  std::vector<std::vector<RaySeg>> per((size_t)n);
+  parallel_for(n, threads, 64, [&](int64_t b, int64_t e, int) {
+    PathCtx ctx;
+    ctx.list.reserve(64);
+    for (int64_t i = b; i < e; i++) {
+      ctx.dump = &per[(size_t)i];
+      const int x = xy[2 * i], y = xy[2 * i + 1];
+      Ray r = get_camera_ray(*s, x, y, sample[i]);
+      double c[3];
+      get_color(*s, r, (uint32_t)(y * s->par.width + x), sample[i], ctx, c, nullptr, 0, nullptr);
+    }
+  });
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; i++)
+    for (const RaySeg& g : per[(size_t)i]) {
+      if (k < capacity) {
+        rays[k].origin[0] = g.ray.o.x; rays[k].origin[1] = g.ray.o.y; rays[k].origin[2] = g.ray.o.z;
+        rays[k].dir[0] = g.ray.d.x; rays[k].dir[1] = g.ray.d.y; rays[k].dir[2] = g.ray.d.z;
+        to_rtc_hit(g.skip, skip[k]);
+        to_rtc_hit(g.hit, hits[k]);
+        bounce[k] = g.bounce;
+      }
+      k++;
+    }
+  return k;
 }
 
 static int intersection_count(const orc_scene& s, int ni, const Ray& ray) {  // BVH.GetIntersectionCount, BVH.cs:352-363

@@ -53,6 +53,12 @@ uint64_t orc_render(orc_scene* s, int32_t x0, int32_t y0, int32_t x1, int32_t y1
 /* One sample of every pixel, raw GetColor output (Placeholder = -1,-1,-1 for misses). out: w*h*3. */
 void orc_render_samples(orc_scene* s, uint32_t sample, int threads, double* out_rgb);
 
+/* The ray batches of SURVEY.md appendix C: every Scene.RayTrace call (Raytracer.cs:77) that GetColor makes for the n paths
+ * (x, y, sample) -- the ray, the skip hit handed in (prim -1 = none), the oracle's answer and the bounce index -- in path
+ * order, bounce order within a path. Returns the number of segments (stores at most `capacity`). */
+int64_t orc_dump_path_rays(orc_scene* s, int64_t n, const int32_t* xy, const uint32_t* sample, int threads, int64_t capacity,
+                           rtc_ray* rays, rtc_hit* skip, rtc_hit* hits, int32_t* bounce);
+
 /* Raytracer.GetDebugTrace(x,y) (Raytracer.cs:254-260). */
 void orc_debug_trace(orc_scene* s, int32_t x, int32_t y, uint32_t sample, int32_t capacity, rtc_debug_ray* out,
                      int32_t* n);

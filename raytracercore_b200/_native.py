@@ -16,7 +16,7 @@ RTC_FLAG_MIRROR, RTC_FLAG_TWOSIDED, RTC_FLAG_INVERT, RTC_FLAG_TRANSFORMED, RTC_F
 RTC_CAMERA_FRUSTUM, RTC_CAMERA_ORTHO = 0, 1
 RTC_GEOM_STRIDE, RTC_MATERIAL_STRIDE, RTC_XFORM_STRIDE = 12, 14, 48
 RTC_K_RAYGEN, RTC_K_TRACE, RTC_K_SHADE, RTC_K_COMPACT, RTC_K_ACCUMULATE, RTC_K_COUNT = 0, 1, 2, 3, 4, 5
-RTC_OPT_KERNEL_TIMING, RTC_OPT_COUNTERS, RTC_OPT_MAX_PATHS, RTC_OPT_SORT_RAYS = 1, 2, 3, 4
+RTC_OPT_KERNEL_TIMING, RTC_OPT_COUNTERS, RTC_OPT_MAX_PATHS = 1, 2, 3
 KERNEL_NAMES = ("raygen", "trace", "shade", "compact", "accumulate")
 BOUNCE_TYPES = ("Skipped", "Diffuse", "Specular", "SpecularFail", "Transmitted", "Emission", "PureBlack",
                 "RecursionComplete", "Missed", "Debug")
@@ -106,6 +106,7 @@ SIGNATURES = {
     "rtc_write_accum": (C.c_int, [_P, _P, _P, _P]),
     "rtc_accum_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "rtc_tonemap_argb": (C.c_int, [_P, C.c_double, C.POINTER(C.c_double), C.c_double, _P]),
+    "rtc_read_pixel": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rtc_debug_trace": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(DebugRay), C.POINTER(C.c_int32)]),
     "rtc_debug_raycast": (C.c_int, [_P, C.c_int32, _P]),
     "rtc_render_samples": (C.c_int, [_P, C.c_uint32, _P]),

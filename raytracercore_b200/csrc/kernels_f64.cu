@@ -78,6 +78,25 @@ cudaError_t launch_overlay_boxcount(cudaStream_t s, const rtc_bvh_node* nodes, i
   return cudaGetLastError();
 }
 
+__global__ void k_subtract_planes(size_t n, double* __restrict__ rgb_sum, uint32_t* __restrict__ samples, uint32_t* __restrict__ misses,
+                                  const double* __restrict__ base_rgb, const uint32_t* __restrict__ base_samples,
+                                  const uint32_t* __restrict__ base_misses) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rgb_sum[i * 3] -= base_rgb[i * 3];
+  rgb_sum[i * 3 + 1] -= base_rgb[i * 3 + 1];
+  rgb_sum[i * 3 + 2] -= base_rgb[i * 3 + 2];
+  samples[i] -= base_samples[i];
+  misses[i] -= base_misses[i];
+}
+
+cudaError_t launch_subtract_planes(cudaStream_t s, size_t n, double* rgb_sum, uint32_t* samples, uint32_t* misses,
+                                   const double* base_rgb, const uint32_t* base_samples, const uint32_t* base_misses) {
+  if (n == 0) return cudaSuccess;
+  k_subtract_planes<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, rgb_sum, samples, misses, base_rgb, base_samples, base_misses);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tonemap(cudaStream_t s, int32_t n, const double* rgb_sum, const uint32_t* samples, const uint32_t* misses,
                            double exposure, double br, double bg, double bb, double ba, uint32_t* argb) {
   if (n <= 0) return cudaSuccess;

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -158,6 +159,11 @@ struct rtc_ctx {
 
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // after an all-reduce every rank holds the job's running total; `base` is a copy of it, subtracted again on ranks != 0
+  // before the next collective so that only the samples rendered since then are contributed (rtc_reduce_accum)
+  bool replicated = false;
+  double* d_base_rgb = nullptr;
+  uint32_t *d_base_samples = nullptr, *d_base_misses = nullptr;
 
   // copy engine choreography: the shading half of a pinned scene image (materials, ids) is copied on a second stream
   // behind the geometry half, so traversal starts while it is still in flight; rtc_render_read streams the finished
@@ -165,6 +171,22 @@ struct rtc_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_geom = nullptr, ev_shading = nullptr, ev_band = nullptr;
   bool shading_pending = false;  // kernels that read materials / ids must first wait for ev_shading
+
+  // UI read-out beside the render loop (rtc_tonemap_argb, rtc_read_pixel): these two calls may come
+  // from a second host thread while the first is inside rtc_render / rtc_sync. They run on their own stream behind the event of
+  // the last accumulate launch issued, into persistent device + pinned staging buffers; the render stream never waits for the
+  // host, only (for the tens of microseconds of a tonemap kernel) the next accumulate launch waits for a read-out in flight.
+  std::mutex ui_mutex;    // serialises the read-out calls (they share the staging buffers)
+  std::mutex ev_mutex;    // guards ev_accum / ev_ui_done bookkeeping between the render thread and the read-out thread
+  cudaStream_t ui_stream = nullptr;
+  cudaEvent_t ev_accum = nullptr, ev_ui_done = nullptr;
+  bool accum_recorded = false, ui_pending = false;
+  uint32_t *d_argb = nullptr, *h_argb = nullptr;  // persistent ARGB8 image: device + pinned host staging
+  size_t argb_cap = 0;
+  double* h_pixel = nullptr;  // pinned: rgb[3] + samples + misses of one pixel
+  // scratch for rtc_render_samples / rtc_debug_raycast (grown on demand, reused)
+  void* d_scratch = nullptr;
+  size_t scratch_cap = 0;
 };
 
 
@@ -187,6 +209,67 @@ int ensure_copy_stream(rtc_ctx* ctx) {
   CU(cudaEventCreateWithFlags(&ctx->ev_geom, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&ctx->ev_shading, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&ctx->ev_band, cudaEventDisableTiming));
+  return RTC_OK;
+}
+
+int ensure_ui_stream(rtc_ctx* ctx) {
+  if (ctx->ui_stream) return RTC_OK;
+  CU(cudaStreamCreateWithFlags(&ctx->ui_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&ctx->ev_accum, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->ev_ui_done, cudaEventDisableTiming));
+  CU(cudaMallocHost((void**)&ctx->h_pixel, 8 * sizeof(double)));
+  return RTC_OK;
+}
+
+int ensure_scratch(rtc_ctx* ctx, size_t bytes) {
+  if (ctx->scratch_cap >= bytes && ctx->d_scratch) return RTC_OK;
+  if (ctx->d_scratch) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr;
+    ctx->scratch_cap = 0;
+  }
+  CU(cudaMalloc(&ctx->d_scratch, bytes));
+  ctx->scratch_cap = bytes;
+  return RTC_OK;
+}
+
+// Render-thread side of the read-out protocol: called right before a launch that writes the accumulation planes ...
+int before_accum_write(rtc_ctx* ctx) {
+  std::lock_guard<std::mutex> g(ctx->ev_mutex);
+  if (ctx->ui_pending) {  // a tonemap / pixel read is (or was) in flight on ui_stream: the planes must not change under it
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_ui_done, 0));
+    ctx->ui_pending = false;
+  }
+  return RTC_OK;
+}
+// ... and right after it
+int after_accum_write(rtc_ctx* ctx) {
+  if (!ctx->ev_accum) return RTC_OK;  // no read-out has ever been asked for
+  std::lock_guard<std::mutex> g(ctx->ev_mutex);
+  CU(cudaEventRecord(ctx->ev_accum, ctx->stream));
+  ctx->accum_recorded = true;
+  return RTC_OK;
+}
+// Read-out side: order ui_stream behind every write to the planes issued so far
+int ui_begin(rtc_ctx* ctx) {
+  int rc = ensure_ui_stream(ctx);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(ctx->ev_mutex);
+  if (!ctx->accum_recorded) {  // first read-out: everything issued on the render stream so far
+    CU(cudaEventRecord(ctx->ev_accum, ctx->stream));
+    ctx->accum_recorded = true;
+  }
+  CU(cudaStreamWaitEvent(ctx->ui_stream, ctx->ev_accum, 0));
+  return RTC_OK;
+}
+int ui_end(rtc_ctx* ctx) {
+  {
+    std::lock_guard<std::mutex> g(ctx->ev_mutex);
+    CU(cudaEventRecord(ctx->ev_ui_done, ctx->ui_stream));
+    ctx->ui_pending = true;
+  }
+  CU(cudaEventSynchronize(ctx->ev_ui_done));
   return RTC_OK;
 }
 
@@ -1118,8 +1201,14 @@ int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb,
     }
   }
   if (accumulate) {
-    Timed t(ctx, RTC_K_ACCUMULATE);
-    CU(Kernels<R>::accumulate(cfg, par, band, pv, ctx->d_rgb, ctx->d_samples, ctx->d_misses));
+    int rcu = before_accum_write(ctx);
+    if (rcu) return rcu;
+    {
+      Timed t(ctx, RTC_K_ACCUMULATE);
+      CU(Kernels<R>::accumulate(cfg, par, band, pv, ctx->d_rgb, ctx->d_samples, ctx->d_misses));
+    }
+    rcu = after_accum_write(ctx);
+    if (rcu) return rcu;
   } else if (d_out_rgb) {
     CU(Kernels<R>::export_radiance(cfg, band, par, pv, d_out_rgb));
   }
@@ -1171,9 +1260,14 @@ int render_rect(rtc_ctx* ctx, int x0, int y0, int x1, int y1, uint32_t first_sam
 int ensure_accum(rtc_ctx* ctx) {
   int w = ctx->par.width, h = ctx->par.height;
   if (ctx->d_rgb && ctx->acc_w == w && ctx->acc_h == h) return RTC_OK;
+  if (ctx->d_rgb) CU(cudaStreamSynchronize(ctx->stream));
   free_dev_t(ctx->d_rgb);
   free_dev_t(ctx->d_samples);
   free_dev_t(ctx->d_misses);
+  free_dev_t(ctx->d_base_rgb);
+  free_dev_t(ctx->d_base_samples);
+  free_dev_t(ctx->d_base_misses);
+  ctx->replicated = false;
   size_t n = (size_t)w * h;
   CU(cudaMalloc((void**)&ctx->d_rgb, n * 3 * sizeof(double)));
   CU(cudaMalloc((void**)&ctx->d_samples, n * sizeof(uint32_t)));
@@ -1306,6 +1400,16 @@ void rtc_destroy(rtc_ctx* ctx) {
     cudaEventDestroy(ctx->ev_shading);
     cudaEventDestroy(ctx->ev_band);
   }
+  if (ctx->ui_stream) {
+    cudaStreamSynchronize(ctx->ui_stream);
+    cudaStreamDestroy(ctx->ui_stream);
+    cudaEventDestroy(ctx->ev_accum);
+    cudaEventDestroy(ctx->ev_ui_done);
+    cudaFreeHost(ctx->h_pixel);
+  }
+  if (ctx->h_argb) cudaFreeHost(ctx->h_argb);
+  free_dev_t(ctx->d_argb);
+  free_dev(ctx->d_scratch);
   rtc_comm_destroy(ctx);
   drain_timing(ctx);
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
@@ -1319,6 +1423,9 @@ void rtc_destroy(rtc_ctx* ctx) {
   free_dev_t(ctx->d_rgb);
   free_dev_t(ctx->d_samples);
   free_dev_t(ctx->d_misses);
+  free_dev_t(ctx->d_base_rgb);
+  free_dev_t(ctx->d_base_samples);
+  free_dev_t(ctx->d_base_misses);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1684,10 +1791,13 @@ int rtc_clear_accum(rtc_ctx* ctx) {
   int rc = ensure_accum(ctx);
   if (rc) return rc;
   size_t n = (size_t)ctx->acc_w * ctx->acc_h;
+  rc = before_accum_write(ctx);
+  if (rc) return rc;
   CU(cudaMemsetAsync(ctx->d_rgb, 0, n * 3 * sizeof(double), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_samples, 0, n * sizeof(uint32_t), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_misses, 0, n * sizeof(uint32_t), ctx->stream));
-  return RTC_OK;
+  ctx->replicated = false;
+  return after_accum_write(ctx);
 }
 
 int rtc_read_accum(rtc_ctx* ctx, double* rgb_sum, uint32_t* samples, uint32_t* misses) {
@@ -1709,11 +1819,14 @@ int rtc_write_accum(rtc_ctx* ctx, const double* rgb_sum, const uint32_t* samples
   if (!ctx->d_rgb) return fail(ctx, RTC_ERR_STATE, "no accumulation buffer (rtc_set_params)");
   cudaSetDevice(ctx->device);
   size_t n = (size_t)ctx->acc_w * ctx->acc_h;
+  int rcw = before_accum_write(ctx);
+  if (rcw) return rcw;
   CU(cudaMemcpyAsync(ctx->d_rgb, rgb_sum, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_samples, samples, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_misses, misses, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  return RTC_OK;
+  ctx->replicated = false;  // the planes are this rank's own contribution again
+  return after_accum_write(ctx);
 }
 
 int rtc_accum_device_ptrs(rtc_ctx* ctx, void** rgb_sum, void** samples, void** misses) {
@@ -1730,14 +1843,50 @@ int rtc_tonemap_argb(rtc_ctx* ctx, double exposure, const double back_rgb[3], do
   if (!back_rgb || !argb) return fail(ctx, RTC_ERR_INVALID, "back_rgb/argb must not be null");
   if (!ctx->d_rgb) return fail(ctx, RTC_ERR_STATE, "no accumulation buffer (rtc_set_params)");
   cudaSetDevice(ctx->device);
-  int32_t n = ctx->acc_w * ctx->acc_h;
-  uint32_t* d = nullptr;
-  CU(cudaMalloc((void**)&d, sizeof(uint32_t) * (size_t)n));
-  cudaError_t e = launch_tonemap(ctx->stream, n, ctx->d_rgb, ctx->d_samples, ctx->d_misses, exposure, back_rgb[0], back_rgb[1], back_rgb[2], back_a, d);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(argb, d, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d);
-  if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("tonemap: ") + cudaGetErrorString(e));
+  std::lock_guard<std::mutex> ui(ctx->ui_mutex);
+  const size_t n = (size_t)ctx->acc_w * ctx->acc_h;
+  if (ctx->argb_cap < n) {  // persistent image buffers, sized once per image size
+    if (ctx->ui_stream) CU(cudaStreamSynchronize(ctx->ui_stream));
+    free_dev_t(ctx->d_argb);
+    if (ctx->h_argb) cudaFreeHost(ctx->h_argb);
+    ctx->h_argb = nullptr;
+    ctx->argb_cap = 0;
+    CU(cudaMalloc((void**)&ctx->d_argb, sizeof(uint32_t) * n));
+    CU(cudaMallocHost((void**)&ctx->h_argb, sizeof(uint32_t) * n));
+    ctx->argb_cap = n;
+  }
+  int rc = ui_begin(ctx);
+  if (rc) return rc;
+  CU(launch_tonemap(ctx->ui_stream, (int32_t)n, ctx->d_rgb, ctx->d_samples, ctx->d_misses, exposure, back_rgb[0], back_rgb[1], back_rgb[2], back_a,
+                    ctx->d_argb));
+  CU(cudaMemcpyAsync(ctx->h_argb, ctx->d_argb, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->ui_stream));
+  rc = ui_end(ctx);
+  if (rc) return rc;
+  std::memcpy(argb, ctx->h_argb, sizeof(uint32_t) * n);
+  return RTC_OK;
+}
+
+int rtc_read_pixel(rtc_ctx* ctx, int32_t x, int32_t y, double rgb_sum[3], uint32_t* samples, uint32_t* misses) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!rgb_sum || !samples || !misses) return fail(ctx, RTC_ERR_INVALID, "rgb_sum/samples/misses must not be null");
+  if (!ctx->d_rgb) return fail(ctx, RTC_ERR_STATE, "no accumulation buffer (rtc_set_params)");
+  if (x < 0 || y < 0 || x >= ctx->acc_w || y >= ctx->acc_h) return fail(ctx, RTC_ERR_INVALID, "pixel outside the image");
+  cudaSetDevice(ctx->device);
+  std::lock_guard<std::mutex> ui(ctx->ui_mutex);
+  int rc = ui_begin(ctx);
+  if (rc) return rc;
+  const size_t i = (size_t)y * ctx->acc_w + x;
+  uint32_t* hu = reinterpret_cast<uint32_t*>(ctx->h_pixel + 3);
+  CU(cudaMemcpyAsync(ctx->h_pixel, ctx->d_rgb + i * 3, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->ui_stream));
+  CU(cudaMemcpyAsync(hu, ctx->d_samples + i, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->ui_stream));
+  CU(cudaMemcpyAsync(hu + 1, ctx->d_misses + i, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->ui_stream));
+  rc = ui_end(ctx);
+  if (rc) return rc;
+  rgb_sum[0] = ctx->h_pixel[0];
+  rgb_sum[1] = ctx->h_pixel[1];
+  rgb_sum[2] = ctx->h_pixel[2];
+  *samples = hu[0];
+  *misses = hu[1];
   return RTC_OK;
 }
 
@@ -1748,14 +1897,14 @@ int rtc_render_samples(rtc_ctx* ctx, uint32_t sample, double* out_rgb) {
   if (rc) return rc;
   cudaSetDevice(ctx->device);
   size_t n = (size_t)ctx->par.width * ctx->par.height;
-  double* d = nullptr;
-  CU(cudaMalloc((void**)&d, n * 3 * sizeof(double)));
+  rc = ensure_scratch(ctx, n * 3 * sizeof(double));
+  if (rc) return rc;
+  double* d = (double*)ctx->d_scratch;
   rc = ctx->precision == RTC_F64 ? render_rect<double>(ctx, 0, 0, ctx->par.width, ctx->par.height, sample, 1, false, d)
                                  : render_rect<float>(ctx, 0, 0, ctx->par.width, ctx->par.height, sample, 1, false, d);
   cudaError_t e = cudaSuccess;
   if (rc == RTC_OK) e = cudaMemcpyAsync(out_rgb, d, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("render_samples: ") + cudaGetErrorString(e));
   return RTC_OK;
@@ -1849,17 +1998,17 @@ int rtc_debug_raycast(rtc_ctx* ctx, int32_t mode, int32_t* out) {
   if (rc) return rc;
   const int w = ctx->par.width, h = ctx->par.height;
   const size_t n = (size_t)w * h;
-  int32_t* d_out = nullptr;
-  CU(cudaMalloc((void**)&d_out, n * sizeof(int32_t)));
+  if (mode == RTC_OVERLAY_BOUNDING_VOLUMES && ctx->nodes.empty())
+    return fail(ctx, RTC_ERR_STATE, "no host-side BVH (the scene came from rtc_upload_baked)");
+  // persistent scratch: [w*h ids | the reference-shaped tree for the box-count mode]
+  const size_t ids_bytes = (n * sizeof(int32_t) + 255) & ~(size_t)255;
+  rc = ensure_scratch(ctx, ids_bytes + (mode == RTC_OVERLAY_BOUNDING_VOLUMES ? ctx->nodes.size() * sizeof(rtc_bvh_node) : 0));
+  if (rc) return rc;
+  int32_t* d_out = (int32_t*)ctx->d_scratch;
   cudaError_t e = cudaSuccess;
-  rtc_bvh_node* d_nodes = nullptr;
+  rtc_bvh_node* d_nodes = (rtc_bvh_node*)((char*)ctx->d_scratch + ids_bytes);
   if (mode == RTC_OVERLAY_BOUNDING_VOLUMES) {
-    if (ctx->nodes.empty()) {
-      cudaFree(d_out);
-      return fail(ctx, RTC_ERR_STATE, "no host-side BVH (the scene came from rtc_upload_baked)");
-    }
-    e = cudaMalloc((void**)&d_nodes, ctx->nodes.size() * sizeof(rtc_bvh_node));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_nodes, ctx->nodes.data(), ctx->nodes.size() * sizeof(rtc_bvh_node), cudaMemcpyHostToDevice, ctx->stream);
+    e = cudaMemcpyAsync(d_nodes, ctx->nodes.data(), ctx->nodes.size() * sizeof(rtc_bvh_node), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = launch_overlay_boxcount(ctx->stream, d_nodes, ctx->root, camera_view<double>(ctx->cam), w, h, d_out);
   } else {
     auto run = [&](auto tag) -> int {
@@ -1888,8 +2037,6 @@ int rtc_debug_raycast(rtc_ctx* ctx, int32_t mode, int32_t* out) {
   if (rc == RTC_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   else cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_out);
-  if (d_nodes) cudaFree(d_nodes);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("debug_raycast: ") + cudaGetErrorString(e));
   return RTC_OK;
@@ -1956,7 +2103,15 @@ int rtc_reduce_accum(rtc_ctx* ctx, int32_t root) {
   if (!ctx->d_rgb) return fail(ctx, RTC_ERR_STATE, "no accumulation buffer (rtc_set_params)");
   if (root >= ctx->nranks) return fail(ctx, RTC_ERR_INVALID, "root out of range");
   cudaSetDevice(ctx->device);
-  size_t n = (size_t)ctx->acc_w * ctx->acc_h;
+  const size_t n = (size_t)ctx->acc_w * ctx->acc_h;
+  int rcw = before_accum_write(ctx);
+  if (rcw) return rcw;
+  // The planes of a rank hold what it has rendered and not yet handed over. After an all-reduce they hold the job's total
+  // on every rank: all but rank 0 take it out again first, so that the total is contributed exactly once.
+  if (ctx->replicated && ctx->rank != 0)
+    CU(launch_subtract_planes(ctx->stream, n, ctx->d_rgb, ctx->d_samples, ctx->d_misses, ctx->d_base_rgb, ctx->d_base_samples,
+                              ctx->d_base_misses));
+  ctx->replicated = false;
   int r = g_nccl.GroupStart();
   if (r == 0) {
     if (root < 0) {
@@ -1972,7 +2127,26 @@ int rtc_reduce_accum(rtc_ctx* ctx, int32_t root) {
     if (r == 0) r = r2;
   }
   if (r != 0) return fail(ctx, RTC_ERR_NCCL, std::string("nccl reduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
-  return RTC_OK;
+  if (root >= 0) {
+    if (ctx->rank != root) {  // the contribution has moved to the root, which keeps the running total
+      CU(cudaMemsetAsync(ctx->d_rgb, 0, n * 3 * sizeof(double), ctx->stream));
+      CU(cudaMemsetAsync(ctx->d_samples, 0, n * sizeof(uint32_t), ctx->stream));
+      CU(cudaMemsetAsync(ctx->d_misses, 0, n * sizeof(uint32_t), ctx->stream));
+    }
+  } else {
+    if (ctx->rank != 0) {
+      if (!ctx->d_base_rgb) {
+        CU(cudaMalloc((void**)&ctx->d_base_rgb, n * 3 * sizeof(double)));
+        CU(cudaMalloc((void**)&ctx->d_base_samples, n * sizeof(uint32_t)));
+        CU(cudaMalloc((void**)&ctx->d_base_misses, n * sizeof(uint32_t)));
+      }
+      CU(cudaMemcpyAsync(ctx->d_base_rgb, ctx->d_rgb, n * 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(ctx->d_base_samples, ctx->d_samples, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(ctx->d_base_misses, ctx->d_misses, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ctx->replicated = true;
+  }
+  return after_accum_write(ctx);
 }
 
 int rtc_comm_destroy(rtc_ctx* ctx) {

@@ -218,6 +218,9 @@ cudaError_t build_bvh_ploc(cudaStream_t stream, int32_t m, const double* boxes, 
                            rtc_bvh_node* nodes_out, int32_t* root_out, int32_t* rounds_out);
 
 // mode-independent
+// planes -= base (rtc_reduce_accum after an all-reduce: only the samples rendered since then are contributed again)
+cudaError_t launch_subtract_planes(cudaStream_t s, size_t n, double* rgb_sum, uint32_t* samples, uint32_t* misses,
+                                   const double* base_rgb, const uint32_t* base_samples, const uint32_t* base_misses);
 cudaError_t launch_tonemap(cudaStream_t s, int32_t n, const double* rgb_sum, const uint32_t* samples,
                            const uint32_t* misses, double exposure, double br, double bg, double bb, double ba,
                            uint32_t* argb);

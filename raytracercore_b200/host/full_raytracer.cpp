@@ -57,25 +57,44 @@ std::string GroupDigits(unsigned long long v) {  // {value:N0}
 }  // namespace
 
 struct rtcs_raytracer {
-  Scene* scene = nullptr;
+  std::shared_ptr<Scene> scene;  // kept alive for as long as the raytracer exists
   rtc_ctx* ctx = nullptr;
   uint64_t seed = 0;
   rtcs_status_fn status = nullptr;
   void* user = nullptr;
-  double Exposure = 1;
+  std::atomic<double> Exposure{1};
+  // Running / Stopping change only under state_mutex: Start's "wait until the previous run is over, then claim the
+  // renderer and clear the stop request" (FullRaytracer.cs:245-250) is one critical section, so two Starts cannot both
+  // proceed and a Stop that arrives after Start has claimed the renderer is never lost. Readers (IsRunning ...) are lock-free.
+  std::mutex state_mutex;
+  std::condition_variable state_cv;
   std::atomic<bool> Stopping{false}, Running{false}, Paused{false};
-  std::mutex ctx_mutex;  // the kernel ABI is single-caller per handle
+  std::mutex ctx_mutex;  // render-side calls of the kernel ABI are single-caller per handle (the read-out calls are exempt)
   std::mutex pause_mutex;
   std::condition_variable pause_cv;
+  std::mutex err_mutex;
   std::string err;
-  bool have_image = false;
+  std::atomic<bool> have_image{false};
 
   void UpdateStatus(const std::string& text, double progress) {  // FullRaytracer.cs:91-94
     if (status) status(user, text.c_str(), progress);
   }
-  int Fail(int rc) {
-    err = rtc_last_error(ctx);
-    Running = false;
+  void SetError(const std::string& m) {
+    std::lock_guard<std::mutex> g(err_mutex);
+    err = m;
+  }
+  void Finish() {  // the end of Start(): `Running = false` (:373), waking a waiting Start / destroy
+    {
+      std::lock_guard<std::mutex> g(state_mutex);
+      Running = false;
+    }
+    state_cv.notify_all();
+  }
+  int Fail(int rc, const char* what = nullptr) {
+    const std::string m = what ? std::string(what) : std::string(rtc_last_error(ctx));
+    SetError(m);
+    UpdateStatus("Error: " + m, 0);  // the reference would surface a .NET exception on the render thread
+    Finish();
     return rc;
   }
 };
@@ -99,7 +118,7 @@ rtcs_raytracer* rtcs_raytracer_create(rtcs_scene* scene, int32_t device, int32_t
     return nullptr;
   }
   rtcs_raytracer* r = new rtcs_raytracer();
-  r->scene = scene->scene.get();
+  r->scene = scene->scene;
   r->ctx = ctx;
   r->seed = seed;
   r->status = status;
@@ -110,7 +129,10 @@ rtcs_raytracer* rtcs_raytracer_create(rtcs_scene* scene, int32_t device, int32_t
 void rtcs_raytracer_destroy(rtcs_raytracer* r) {
   if (!r) return;
   rtcs_raytracer_stop(r);
-  while (r->Running) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  {
+    std::unique_lock<std::mutex> lk(r->state_mutex);
+    r->state_cv.wait(lk, [&] { return !r->Running.load(); });
+  }
   rtc_destroy(r->ctx);
   delete r;
 }
@@ -118,9 +140,12 @@ void rtcs_raytracer_destroy(rtcs_raytracer* r) {
 int rtcs_raytracer_start(rtcs_raytracer* r, uint32_t samples_per_pass, uint32_t max_samples) {
   if (!r) return RTC_ERR_INVALID;
   if (samples_per_pass == 0) samples_per_pass = 1;
-  while (r->Running) std::this_thread::yield();  // FullRaytracer.cs:245
-  r->Stopping = false;
-  r->Running = true;
+  {
+    std::unique_lock<std::mutex> lk(r->state_mutex);
+    r->state_cv.wait(lk, [&] { return !r->Running.load(); });  // `while (Running) ;` FullRaytracer.cs:245
+    r->Running = true;                                         // :249-250, as one step with the wait
+    r->Stopping = false;
+  }
   Scene& sc = *r->scene;
   r->UpdateStatus("Preparing scene...", 0);  // :252
   int rc;
@@ -139,11 +164,7 @@ int rtcs_raytracer_start(rtcs_raytracer* r, uint32_t samples_per_pass, uint32_t 
     if (rc) return r->Fail(rc);
     rc = rtc_clear_accum(r->ctx);
     if (rc) return r->Fail(rc);
-    if (sc.Cameras.empty()) {
-      r->err = "scene has no camera";
-      r->Running = false;
-      return RTC_ERR_STATE;
-    }
+    if (sc.Cameras.empty()) return r->Fail(RTC_ERR_STATE, "scene has no camera");
     rtc_camera cam = sc.Cameras[sc.CurrentCamera].InitRender(sc.Width, sc.Height);
     rc = rtc_set_camera(r->ctx, &cam);
     if (rc) return r->Fail(rc);
@@ -184,13 +205,16 @@ int rtcs_raytracer_start(rtcs_raytracer* r, uint32_t samples_per_pass, uint32_t 
                   FormatTimeSpan(total_seconds).c_str(), perPixel, samplesPerSecond);
     r->UpdateStatus(buf, progress);
   }
-  r->Running = false;
+  r->Finish();
   return RTC_OK;
 }
 
 void rtcs_raytracer_stop(rtcs_raytracer* r) {  // :409-414
   if (!r) return;
-  r->Stopping = true;
+  {
+    std::lock_guard<std::mutex> g(r->state_mutex);
+    r->Stopping = true;
+  }
   rtcs_raytracer_resume(r);
 }
 void rtcs_raytracer_pause(rtcs_raytracer* r) {
@@ -221,42 +245,34 @@ int rtcs_raytracer_get_sample_set(rtcs_raytracer* r, int32_t x, int32_t y, doubl
   // reference, so the mirror clamps to the last pixel.
   x = std::min(std::max(x, 0), sc.Width - 1);
   y = std::min(std::max(y, 0), sc.Height - 1);
-  size_t n = (size_t)sc.Width * sc.Height;
-  std::vector<double> c(n * 3);
-  std::vector<uint32_t> s(n), m(n);
-  int rc;
-  {
-    std::lock_guard<std::mutex> g(r->ctx_mutex);
-    rc = rtc_read_accum(r->ctx, c.data(), s.data(), m.data());
-  }
-  if (rc) {
-    r->err = rtc_last_error(r->ctx);
-    return rc;
-  }
-  size_t i = (size_t)y * sc.Width + x;
-  rgb[0] = c[i * 3];
-  rgb[1] = c[i * 3 + 1];
-  rgb[2] = c[i * 3 + 2];
-  *samples = s[i];
-  *misses = m[i];
-  return RTC_OK;
+  // one pixel on the read-out stream: no lock against the render loop, no full-image copy (MainWindow.cs:360-370 calls this
+  // on every mouse move)
+  int rc = rtc_read_pixel(r->ctx, x, y, rgb, samples, misses);
+  if (rc) r->SetError(rtc_last_error(r->ctx));
+  return rc;
 }
 
 int rtcs_raytracer_get_bitmap(rtcs_raytracer* r, uint32_t* argb) {
   if (!r || !argb) return RTC_ERR_INVALID;
   if (!r->have_image) {
-    r->err = "nothing rendered yet";
+    r->SetError("nothing rendered yet");
     return RTC_ERR_STATE;  // GetBitmap returns null when SampleSets == null (:184-185)
   }
   Scene& sc = *r->scene;
   double back[3] = {sc.BackgroundRGB.R, sc.BackgroundRGB.G, sc.BackgroundRGB.B};
-  std::lock_guard<std::mutex> g(r->ctx_mutex);
-  int rc = rtc_tonemap_argb(r->ctx, r->Exposure, back, sc.BackgroundAlpha, argb);
-  if (rc) r->err = rtc_last_error(r->ctx);
+  // read-out call: runs beside the render loop without taking its lock (rtcore_b200.h, rtc_tonemap_argb)
+  int rc = rtc_tonemap_argb(r->ctx, r->Exposure.load(), back, sc.BackgroundAlpha, argb);
+  if (rc) r->SetError(rtc_last_error(r->ctx));
   return rc;
 }
 
 rtc_ctx* rtcs_raytracer_ctx(rtcs_raytracer* r) { return r ? r->ctx : nullptr; }
-const char* rtcs_raytracer_last_error(rtcs_raytracer* r) { return r ? r->err.c_str() : ""; }
+const char* rtcs_raytracer_last_error(rtcs_raytracer* r) {
+  if (!r) return "";
+  static thread_local std::string copy;  // the caller's own copy: another thread may replace r->err meanwhile
+  std::lock_guard<std::mutex> g(r->err_mutex);
+  copy = r->err;
+  return copy.c_str();
+}
 
 }  // extern "C"

@@ -138,5 +138,6 @@ std::unique_ptr<Scene> MakeSynthetic(const std::string& name, int64_t n, uint64_
 
 // Handle type of the C façade (include/rtcore_host.h).
 struct rtcs_scene {
-  std::unique_ptr<rtcore::Scene> scene;
+  std::shared_ptr<rtcore::Scene> scene;  // shared with every rtcs_raytracer created over it: freeing the handle does not pull
+                                         // the scene from under a running render
 };

@@ -198,6 +198,13 @@ class Context:
         self._ck(N.lib.rtc_tonemap_argb(self._h, exposure, b, back_a, _ptr(out)))
         return out
 
+    def read_pixel(self, x, y):
+        """FullRaytracer.GetSampleSet(x, y): (rgb sum, samples, misses) of one pixel, on the read-out stream."""
+        rgb = (C.c_double * 3)()
+        s, m = C.c_uint32(), C.c_uint32()
+        self._ck(N.lib.rtc_read_pixel(self._h, x, y, rgb, C.byref(s), C.byref(m)))
+        return tuple(rgb[:]), s.value, m.value
+
     def render_samples(self, sample):
         out = np.zeros((self.height, self.width, 3), dtype=np.float64)
         self._ck(N.lib.rtc_render_samples(self._h, sample, _ptr(out)))

@@ -31,6 +31,8 @@ def _load():
     lib.orc_render_samples.argtypes = [P, C.c_uint32, C.c_int, P]
     lib.orc_debug_trace.argtypes = [P, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(N.DebugRay), C.POINTER(C.c_int32)]
     lib.orc_debug_raycast.argtypes = [P, C.c_int32, P]
+    lib.orc_dump_path_rays.restype = C.c_int64
+    lib.orc_dump_path_rays.argtypes = [P, C.c_int64, P, P, C.c_int, C.c_int64, P, P, P, P]
     lib.orc_tonemap.argtypes = [C.c_int32, C.c_int32, P, P, P, C.c_double, C.POINTER(C.c_double), C.c_double, P]
     lib.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.orc_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
@@ -110,6 +112,17 @@ class OracleScene:
         out = np.zeros((self.height, self.width, 3))
         lib.orc_render_samples(self._h, sample, threads, _ptr(out))
         return out
+
+    def dump_path_rays(self, xy, sample, threads=NTHREADS):
+        """Every Scene.RayTrace call GetColor makes for the paths (x, y, sample): (rays, skip hits, oracle hits, bounce)."""
+        xy = np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
+        sample = np.ascontiguousarray(sample, dtype=np.uint32)
+        cap = len(xy) * (self.params.recursion + 1)
+        rays, skip, hits = np.zeros(cap, RAY_DT), np.zeros(cap, HIT_DT), np.zeros(cap, HIT_DT)
+        bounce = np.zeros(cap, np.int32)
+        n = lib.orc_dump_path_rays(self._h, len(xy), _ptr(xy), _ptr(sample), threads, cap, _ptr(rays), _ptr(skip), _ptr(hits), _ptr(bounce))
+        assert 0 <= n <= cap
+        return rays[:n], skip[:n], hits[:n], bounce[:n]
 
     def debug_raycast(self, mode):
         out = np.zeros((self.height, self.width), dtype=np.int32)

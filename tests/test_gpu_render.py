@@ -415,3 +415,55 @@ def test_debug_raycaster_overlays():
             else:
                 assert (got_p != want_p).mean() < 0.01  # unjittered rays land exactly on shared edges: f32 ties
             ctx.close()
+
+
+def test_ui_read_out_runs_beside_the_render_loop():
+    """GetBitmap / GetSampleSet (rtc_tonemap_argb, rtc_read_pixel) polled from a second thread every
+    few milliseconds while the first thread renders: results stay consistent (a read-out sees whole accumulation passes only),
+    the final image equals an unpolled render bit for bit, and the render loop is not slowed down."""
+    sc = cornell(256, 256, 6)
+    spp, passes = 4, 24
+    ctx = Context(0, RTC_F32)
+    ctx.load(sc, seed=2)
+    ctx.render(0, 1)
+    ctx.sync()
+
+    def run(poll):
+        ctx.clear_accum()
+        ctx.sync()
+        stop = threading.Event()
+        seen = []
+
+        def poller():
+            while not stop.is_set():
+                img = ctx.tonemap(1.0, (0, 0, 0), 0.0)
+                rgb, s, m = ctx.read_pixel(128, 200)
+                seen.append((s + m, int(img[200, 128])))
+                time.sleep(0.003)
+
+        th = threading.Thread(target=poller)
+        if poll:
+            th.start()
+        t0 = time.time()
+        for i in range(passes):
+            ctx.render(i * spp, spp)
+            ctx.sync()
+        dt = time.time() - t0
+        stop.set()
+        if poll:
+            th.join()
+        return dt, seen, ctx.read_accum()
+
+    run(False)  # warm-up
+    t_plain, _, want = run(False)
+    t_poll, seen, got = run(True)
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    assert len(seen) >= 3
+    counts = [c for c, _ in seen]
+    assert all(c % spp == 0 and 0 <= c <= passes * spp for c in counts) and counts == sorted(counts)  # whole passes, monotone
+    print("render loop: %.1f ms unpolled, %.1f ms with %d read-outs" % (t_plain * 1e3, t_poll * 1e3, len(seen)))
+    assert t_poll <= 1.3 * t_plain + 0.02
+    # the read-out equals the synchronous path
+    rgb, s, m = ctx.read_pixel(128, 200)
+    assert np.array_equal(np.array(rgb), got[0][200, 128]) and s == got[1][200, 128] and m == got[2][200, 128]
+    ctx.close()

@@ -63,3 +63,15 @@ def test_two_rank_sample_partition_equals_single_rank(tmp_path):
     rgb, s, m, _ = O.OracleScene(sc, seed=9).render(0, world * spp * frames, threads=1)
     assert np.array_equal(got["s"], s) and np.array_equal(got["m"], m)
     assert np.allclose(got["rgb"], rgb, rtol=1e-12, atol=1e-12)
+
+
+def test_strong_split_tiles_every_frame_exactly():
+    from raytracercore_b200.partition import strong_sample_range
+    for world in (1, 2, 3, 4, 8):
+        for total in (1, 4, 7, 8, 16, 4096):
+            for f in range(3):
+                got = []
+                for r in range(world):
+                    first, n = strong_sample_range(f, r, world, total)
+                    got += list(range(first, first + n))
+                assert got == list(range(f * total, (f + 1) * total)), (world, total, f)
