@@ -381,7 +381,21 @@ inline int plane_hits(const Prim& p, int id, const Ray& ray, Hit out[2]) {
 }
 
 // Util.RayHitMatches (Util.cs:179-192)
-inline bool ray_hit_matches(const Ray& ray, const Hit& a, const Hit& b) {
+// orc_set_selfhit_mode: 0 = the reference's rule (default). 1 = the documented self-hit rule of the library's f32 mode
+// (deviation 1), restated here in f64 so that a test can tell that deviation apart from everything else:
+// a flat primitive equal to the skip hit's primitive is always the self-hit; spheres keep the positional rule with a relative
+// threshold of 1e-9 on squared distances instead of Util.NearEnough = 1e-24.
+int g_selfhit_mode = 0;
+
+inline bool ray_hit_matches(const Ray& ray, const Hit& a, const Hit& b, int kind) {
+  if (g_selfhit_mode == 1) {
+    if (a.prim < 0 || b.prim < 0 || a.prim != b.prim) return false;
+    if (kind != RTC_KIND_SPHERE) return true;
+    const double la = sqlen(a.pos), lb = sqlen(b.pos), ld = sqlen(a.pos - b.pos);
+    if (!(ld == 0 || ld / std::max(la, lb) < 1e-9)) return false;
+    if (dot(ray.d, b.normal) > 0) return a.inside != b.inside;
+    return a.inside == b.inside;
+  }
   if (hit_equal(a, b)) return true;
   if (a.prim < 0 || b.prim < 0) return false;
   if (a.prim != b.prim) return false;
@@ -403,7 +417,7 @@ inline Hit primitive_ray_trace(const Prim& p, int id, const Ray& ray, const Hit&
     Hit cur = hits[i];
     if (p.invert()) cur.inside = !cur.inside;                       // :60-61, Hit.cs:39-42
     if (cur.inside && !p.two_sided()) continue;                     // :63-64
-    if (!ray_hit_matches(ray, cur, skip)) return cur;               // :66-70
+    if (!ray_hit_matches(ray, cur, skip, p.kind)) return cur;       // :66-70
   }
   return Hit{};
 }
@@ -784,6 +798,7 @@ orc_scene* orc_scene_create(const rtc_scene_desc* d, int32_t n_nodes, const rtc_
 void orc_scene_destroy(orc_scene* s) { delete s; }
 void orc_set_camera(orc_scene* s, const rtc_camera* camera) { s->cam = *camera; }
 void orc_set_params(orc_scene* s, const rtc_params* params) { s->par = *params; }
+void orc_set_selfhit_mode(int mode) { g_selfhit_mode = mode; }
 
 int64_t orc_trace_closest(orc_scene* s, int64_t n, const rtc_ray* rays, const rtc_hit* skip, rtc_hit* out, int mode,
                           int check_both, int threads) {

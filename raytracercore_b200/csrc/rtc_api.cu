@@ -1,6 +1,7 @@
 // rtc_api.cu — the C ABI of include/rtcore_b200.h: context, scene hand-over (host f64 arrays -> device SoA +
 // flattened BVH), the wavefront loop that sequences the kernels, accumulation-buffer I/O, stats and the
 // per-frame NCCL collective. Kernels live in kernels_f32.cu / kernels_f64.cu (rtc_device.cuh).
+#include <cuda_fp16.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -74,7 +75,7 @@ struct TimedLaunch {
 // Host-resident image of the device scene layout (one pinned buffer + segment table): what Scene.Prepare leaves
 // behind on the host side, uploadable with plain H2D copies.
 struct rtc_baked {
-  enum { S_NODES, S_QNODES, S_UNBOUNDED, S_PRIMS, S_MATS, S_XFORMS, S_AUX, S_PRIM_ID, S_ID_TO_SLOT, S_PRIM_NZ, S_COUNT };
+  enum { S_NODES, S_QNODES, S_UNBOUNDED, S_PRIMS, S_MATS, S_XFORMS, S_AUX, S_PRIM_ID, S_ID_TO_SLOT, S_SGEOM, S_COUNT };
   int precision = RTC_F32;
   int32_t n_prims = 0, n_unbounded = 0, n_xforms = 0, bvh_depth = 0;
   uint32_t root_node = 0;
@@ -123,7 +124,7 @@ struct rtc_ctx {
   // device scene
   void *d_nodes = nullptr, *d_prims = nullptr, *d_xforms = nullptr, *d_mats = nullptr;
   int32_t *d_aux = nullptr, *d_prim_id = nullptr, *d_id_to_slot = nullptr;
-  void* d_prim_nz = nullptr;
+  void* d_sgeom = nullptr;
   void* d_qnodes = nullptr;       // f32 mode: CNode[]
   uint32_t* d_unbounded = nullptr;  // f32 mode: leaf refs of primitives with infinite boxes
   int32_t n_unbounded = 0;
@@ -135,8 +136,8 @@ struct rtc_ctx {
   // path pool
   int64_t max_paths = 1 << 25;
   int64_t pool_cap = 0;
-  void *d_dir = nullptr, *d_tint = nullptr, *d_hpos[2] = {nullptr, nullptr}, *d_hnrm[2] = {nullptr, nullptr},
-       *d_radiance = nullptr, *d_skip_pos = nullptr;
+  void *d_dir = nullptr, *d_tint = nullptr, *d_hpos = nullptr, *d_hnrm = nullptr, *d_thit = nullptr, *d_radiance = nullptr,
+       *d_skip_pos = nullptr;
   uint32_t* d_queue[2] = {nullptr, nullptr};
   Control* d_ctl = nullptr;
   int32_t* d_dbg_type = nullptr;
@@ -301,7 +302,7 @@ void free_scene_device(rtc_ctx* c) {
   free_dev_t(c->d_aux);
   free_dev_t(c->d_prim_id);
   free_dev_t(c->d_id_to_slot);
-  free_dev_t(c->d_prim_nz);
+  free_dev(c->d_sgeom);
   free_dev(c->d_qnodes);
   free_dev_t(c->d_unbounded);
   c->n_unbounded = 0;
@@ -311,11 +312,10 @@ void free_scene_device(rtc_ctx* c) {
 void free_pool(rtc_ctx* c) {
   free_dev(c->d_dir);
   free_dev(c->d_tint);
-  for (int i = 0; i < 2; i++) {
-    free_dev(c->d_hpos[i]);
-    free_dev(c->d_hnrm[i]);
-    free_dev_t(c->d_queue[i]);
-  }
+  free_dev(c->d_hpos);
+  free_dev(c->d_hnrm);
+  free_dev(c->d_thit);
+  for (int i = 0; i < 2; i++) free_dev_t(c->d_queue[i]);
   free_dev(c->d_radiance);
   free_dev(c->d_skip_pos);
   free_dev_t(c->d_dbg_type);
@@ -333,11 +333,10 @@ int ensure_pool(rtc_ctx* ctx, int64_t want) {
   size_t v4 = rsize(ctx) * 4;
   CU(cudaMalloc(&ctx->d_dir, v4 * want));
   CU(cudaMalloc(&ctx->d_tint, v4 * want));
-  for (int i = 0; i < 2; i++) {
-    CU(cudaMalloc(&ctx->d_hpos[i], v4 * want));
-    CU(cudaMalloc(&ctx->d_hnrm[i], v4 * want));
-    CU(cudaMalloc((void**)&ctx->d_queue[i], sizeof(uint32_t) * want));
-  }
+  CU(cudaMalloc(&ctx->d_hpos, v4 * want));
+  CU(cudaMalloc(&ctx->d_hnrm, v4 * want));
+  CU(cudaMalloc(&ctx->d_thit, (ctx->precision == RTC_F64 ? sizeof(THit<double>) : sizeof(THit<float>)) * want));
+  for (int i = 0; i < 2; i++) CU(cudaMalloc((void**)&ctx->d_queue[i], sizeof(uint32_t) * want));
   CU(cudaMalloc(&ctx->d_radiance, v4 * want));
   if (!ctx->d_ctl) {
     CU(cudaMalloc((void**)&ctx->d_ctl, sizeof(Control)));
@@ -352,11 +351,10 @@ PathView<R> path_view(rtc_ctx* c) {
   PathView<R> pv;
   pv.dir = (V4<R>*)c->d_dir;
   pv.tint = (V4<R>*)c->d_tint;
-  for (int i = 0; i < 2; i++) {
-    pv.hpos[i] = (V4<R>*)c->d_hpos[i];
-    pv.hnrm[i] = (V4<R>*)c->d_hnrm[i];
-    pv.queue[i] = c->d_queue[i];
-  }
+  pv.hpos = (V4<R>*)c->d_hpos;
+  pv.hnrm = (V4<R>*)c->d_hnrm;
+  pv.thit = (THit<R>*)c->d_thit;
+  for (int i = 0; i < 2; i++) pv.queue[i] = c->d_queue[i];
   pv.radiance = (V4<R>*)c->d_radiance;
   pv.skip_pos = nullptr;
   pv.ctl = c->d_ctl;
@@ -374,7 +372,7 @@ SceneView<R> scene_view(rtc_ctx* c) {
   sv.mats = (const DMat<R>*)c->d_mats;
   sv.aux = c->d_aux;
   sv.prim_id = c->d_prim_id;
-  sv.prim_nz = (const R*)c->d_prim_nz;
+  sv.sgeom = (const V4<R>*)c->d_sgeom;
   sv.root = c->root_node;
   sv.n_prims = c->n_prims;
   sv.qnodes = (const CNode*)c->d_qnodes;
@@ -455,7 +453,7 @@ R round_up(double x) {
 int upload_baked_image(rtc_ctx* ctx, const rtc_baked* bk) {
   void** dst[rtc_baked::S_COUNT] = {&ctx->d_nodes, &ctx->d_qnodes, (void**)&ctx->d_unbounded, &ctx->d_prims, &ctx->d_mats,
                                     &ctx->d_xforms, (void**)&ctx->d_aux, (void**)&ctx->d_prim_id, (void**)&ctx->d_id_to_slot,
-                                    &ctx->d_prim_nz};
+                                    &ctx->d_sgeom};
   const bool shading_seg[rtc_baked::S_COUNT] = {false, false, false, false, true, false, false, true, true, true};
   const bool split = bk->pinned;
   if (split) {
@@ -589,6 +587,29 @@ struct PhaseTimer {
     if (on && !log.empty()) std::fprintf(stderr, "[rtcore_b200] flatten:%s\n", log.c_str());
   }
 };
+
+// Material record of one slot from the flattened description (14 doubles, rtcore_b200.h). f32 mode: 12 halfs + 2 floats.
+inline void pack_material(DMat<double>& d, const double* m, bool reflective) {
+  d.emis_ior = V4<double>{m[0], m[1], m[2], m[12]};
+  d.diff_shin = V4<double>{m[3], m[4], m[5], m[13]};
+  d.spec = reflective ? V4<double>{m[6], m[7], m[8], 0} : V4<double>{0, 0, 0, 0};
+  d.refr = reflective ? V4<double>{m[9], m[10], m[11], 0} : V4<double>{0, 0, 0, 0};
+}
+inline uint32_t half_bits(double v) {
+  if (std::isfinite(v)) v = std::min(std::max(v, -65504.0), 65504.0);  // largest finite half: colours beyond it saturate
+  const __half h = __float2half_rn((float)v);
+  uint16_t b;
+  std::memcpy(&b, &h, 2);
+  return b;
+}
+inline void pack_material(DMat<float>& d, const double* m, bool reflective) {
+  double c[12];
+  for (int i = 0; i < 12; i++) c[i] = (i >= 6 && !reflective) ? 0.0 : m[i];
+  for (int i = 0; i < 6; i++) d.w[i] = half_bits(c[2 * i]) | (half_bits(c[2 * i + 1]) << 16);
+  const float ior = (float)m[12], shin = (float)m[13];
+  std::memcpy(&d.w[6], &ior, 4);
+  std::memcpy(&d.w[7], &shin, 4);
+}
 
 template <typename R>
 int build_device_scene(rtc_ctx* ctx) {
@@ -1012,7 +1033,7 @@ int build_device_scene(rtc_ctx* ctx) {
   std::vector<DMat<R>> dm(n);
   std::vector<int32_t> aux(n, -1), prim_id(n), id_to_slot(n);
   std::vector<uint32_t> prim_ref(n);
-  std::vector<R> prim_nz(n, R(0));
+  std::vector<V4<R>> sgeom(n);
   for (int32_t i = 0; i < nn; i++) {
     if (leaf_slot[i] < 0) continue;
     prim_ref[leaf_slot[i]] = leaf_ref(i);
@@ -1031,20 +1052,19 @@ int build_device_scene(rtc_ctx* ctx) {
       d.a.x = (R)g[0]; d.a.y = (R)g[1]; d.a.z = (R)g[2]; d.a.w = (R)g[9];
       d.b.x = (R)g[3]; d.b.y = (R)g[4]; d.b.z = (R)g[5]; d.b.w = (R)g[10];
       d.c.x = (R)g[6]; d.c.y = (R)g[7]; d.c.z = (R)g[8];
-      prim_nz[s] = (R)g[11];
       if ((f & RTC_FLAG_VNORMALS) && ctx->xform[p] >= 0) aux[s] = ctx->xform[p] | (int32_t)REF_VNORMALS_AUX;
+      // shading geometry: the face normal and a flag word (1 = vertex normals: the record must be re-evaluated)
+      sgeom[s] = V4<R>{(R)g[9], (R)g[10], (R)g[11], R(0)};
+      set_ref_bits(sgeom[s].w, aux[s] >= 0 ? 1u : 0u);
     } else {
       d.a.x = (R)g[0]; d.a.y = (R)g[1]; d.a.z = (R)g[2]; d.a.w = (R)g[3];
       if (k == RTC_KIND_SPHERE && (f & RTC_FLAG_TRANSFORMED) && ctx->xform[p] >= 0) aux[s] = ctx->xform[p];
+      sgeom[s] = V4<R>{(R)g[0], (R)g[1], (R)g[2], k == RTC_KIND_SPHERE ? (R)g[3] : R(0)};  // sphere: centre, radius; plane: normal
     }
     set_ref_bits(d.c.w, prim_ref[s]);  // the leaf reference rides in the record (one round trip per leaf test)
     const double* m = &ctx->material[(size_t)p * RTC_MATERIAL_STRIDE];
-    DMat<R>& dmat = dm[s];
     bool reflective = m[13] > 0;  // Primitive.IsReflective (Primitive.cs:106): Specular/Refraction read black otherwise
-    dmat.emis_ior = V4<R>{(R)m[0], (R)m[1], (R)m[2], (R)m[12]};
-    dmat.diff_shin = V4<R>{(R)m[3], (R)m[4], (R)m[5], (R)m[13]};
-    dmat.spec = reflective ? V4<R>{(R)m[6], (R)m[7], (R)m[8], R(0)} : V4<R>{R(0), R(0), R(0), R(0)};
-    dmat.refr = reflective ? V4<R>{(R)m[9], (R)m[10], (R)m[11], R(0)} : V4<R>{R(0), R(0), R(0), R(0)};
+    pack_material(dm[s], m, reflective);
   });
   std::vector<DXform<R>> dx(std::max(1, ctx->n_xforms));
   std::memset(dx.data(), 0, dx.size() * sizeof(DXform<R>));
@@ -1074,11 +1094,11 @@ int build_device_scene(rtc_ctx* ctx) {
   bk->bvh_depth = ctx->bvh_depth;
   bk->root_node = ctx->root_node;
   const void* src[rtc_baked::S_COUNT] = {dn.data(), qn.data(), unbounded.data(), dp.data(), dm.data(), dx.data(),
-                                         aux.data(), prim_id.data(), id_to_slot.data(), prim_nz.data()};
+                                         aux.data(), prim_id.data(), id_to_slot.data(), sgeom.data()};
   const size_t sz[rtc_baked::S_COUNT] = {dn.size() * sizeof(DNode<R>), qn.size() * sizeof(CNode), unbounded.size() * sizeof(uint32_t),
                                          dp.size() * sizeof(DPrim<R>), dm.size() * sizeof(DMat<R>), dx.size() * sizeof(DXform<R>),
                                          aux.size() * sizeof(int32_t), prim_id.size() * sizeof(int32_t),
-                                         id_to_slot.size() * sizeof(int32_t), prim_nz.size() * sizeof(R)};
+                                         id_to_slot.size() * sizeof(int32_t), sgeom.size() * sizeof(V4<R>)};
   size_t total = 0;
   for (int i = 0; i < rtc_baked::S_COUNT; i++) {
     bk->off[i] = total;
@@ -1181,11 +1201,10 @@ int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb,
   const int bounces = std::max(0, ctx->par.recursion) + 1;
   for (int i = 0; i < bounces; i++) {
     const int q = i & 1;
-    const int cur = i & 1, prev = cur ^ 1;  // raygen seeds buffer 1 as the "previous hit" of bounce 0
     const bool ident = (i == 0);
     {
       Timed t(ctx, RTC_K_TRACE);
-      CU(Kernels<R>::trace(cfg, sv, pv, q, prev, cur, ident));
+      CU(Kernels<R>::trace(cfg, sv, pv, q, ident));
     }
     if (i == 0) {
       int rcw = wait_shading_upload(ctx);  // materials may still be arriving behind the first trace launch
@@ -1193,7 +1212,7 @@ int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb,
     }
     {
       Timed t(ctx, RTC_K_SHADE);
-      CU(Kernels<R>::shade(cfg, sv, par, band, pv, q, cur, i, ident));
+      CU(Kernels<R>::shade(cfg, sv, par, band, pv, q, i, ident));
     }
     {
       Timed t(ctx, RTC_K_COMPACT);
@@ -1303,13 +1322,13 @@ int trace_batch(rtc_ctx* ctx, int64_t n, const rtc_ray* rays, const rtc_hit* ski
     int64_t m = std::min(ctx->stage_cap, n - off);
     CU(cudaMemcpyAsync(ctx->d_rays, rays + off, sizeof(rtc_ray) * m, cudaMemcpyHostToDevice, ctx->stream));
     if (skip) CU(cudaMemcpyAsync(ctx->d_skip, skip + off, sizeof(rtc_hit) * m, cudaMemcpyHostToDevice, ctx->stream));
-    CU(Kernels<R>::import_rays(cfg, sv, m, ctx->d_rays, skip ? ctx->d_skip : nullptr, ctx->d_id_to_slot, pv, 1));
+    CU(Kernels<R>::import_rays(cfg, sv, m, ctx->d_rays, skip ? ctx->d_skip : nullptr, ctx->d_id_to_slot, pv));
     {
       Timed t(ctx, RTC_K_TRACE);
-      CU(Kernels<R>::trace(cfg, sv, pv, 0, 1, 0, true));
+      CU(Kernels<R>::trace(cfg, sv, pv, 0, true));
     }
     ctx->stats.rays += (uint64_t)m;
-    CU(Kernels<R>::export_hits(cfg, sv, m, pv, 0, ctx->d_hits, true));
+    CU(Kernels<R>::export_hits(cfg, sv, m, pv, ctx->d_hits, true));
     CU(cudaMemcpyAsync(out + off, ctx->d_hits, sizeof(rtc_hit) * m, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
   }
@@ -1948,17 +1967,15 @@ int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t
       pv.dbg_type = ctx->d_dbg_type;
       pv.dbg_fresnel = (R*)ctx->d_dbg_fresnel;
       CU(Kernels<R>::raygen(cfg, camera_view<R>(ctx->cam), params_view<R>(ctx->par), b, pv));
-      int cur = 0;
       for (int k = 0; k <= i; k++) {
-        cur = k & 1;
-        CU(Kernels<R>::trace(cfg, sv, pv, k & 1, cur ^ 1, cur, k == 0));
-        CU(Kernels<R>::shade(cfg, sv, params_view<R>(ctx->par), b, pv, k & 1, cur, k, k == 0));
+        CU(Kernels<R>::trace(cfg, sv, pv, k & 1, k == 0));
+        CU(Kernels<R>::shade(cfg, sv, params_view<R>(ctx->par), b, pv, k & 1, k, k == 0));
         if (k < i) CU(Kernels<R>::compact(cfg, pv, k & 1, k == 0));
       }
       if (!ctx->d_hits) {
         CU(cudaMalloc((void**)&ctx->d_hits, sizeof(rtc_hit) * 1024));
       }
-      CU(Kernels<R>::export_hits(cfg, sv, 1, pv, cur, ctx->d_hits, false));
+      CU(Kernels<R>::export_hits(cfg, sv, 1, pv, ctx->d_hits, false));
       CU(cudaMemcpyAsync(hits.data(), ctx->d_hits, sizeof(rtc_hit), cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaMemcpyAsync(&type, ctx->d_dbg_type, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
       if (sizeof(R) == 8)
@@ -2027,8 +2044,8 @@ int rtc_debug_raycast(rtc_ctx* ctx, int32_t mode, int32_t* out) {
         b.n_pix = (uint32_t)(w * (b.y1 - b.y0));
         b.n_paths = b.n_pix;
         CU(Kernels<R>::overlay_rays(cfg, camera_view<R>(ctx->cam), params_view<R>(ctx->par), b, pv));
-        CU(Kernels<R>::trace(cfg, sv, pv, 0, 1, 0, true));
-        CU(Kernels<R>::overlay_prims(cfg, sv, params_view<R>(ctx->par), b, pv, 0, d_out));
+        CU(Kernels<R>::trace(cfg, sv, pv, 0, true));
+        CU(Kernels<R>::overlay_prims(cfg, sv, params_view<R>(ctx->par), b, pv, d_out));
       }
       return RTC_OK;
     };

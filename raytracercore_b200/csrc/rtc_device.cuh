@@ -344,7 +344,7 @@ __device__ __forceinline__ int tri_hits(const SceneView<R>& sc, uint32_t ref, co
   if (with_pos<R, WITH_NORMAL>())
     out[0].pos = mk3(rfma(e1.x, u, rfma(e2.x, v, v0.x)), rfma(e1.y, u, rfma(e2.y, v, v0.y)), rfma(e1.z, u, rfma(e2.z, v, v0.z)));  // :130
   if (WITH_NORMAL) {
-    V3<R> N = mk3(A.w, B.w, __ldg(&sc.prim_nz[slot]));
+    V3<R> N = xyz(ldg4(&sc.sgeom[slot]));
     int32_t ax = sc.aux[slot];
     if (ax >= 0 && (ax & REF_VNORMALS_AUX)) {  // :211-219 (weights and the zero face normal are the reference's)
       const DXform<R>* xf = sc.xforms + (ax & 0x3FFFFFFF);
@@ -364,8 +364,10 @@ __device__ __forceinline__ int tri_hits(const SceneView<R>& sc, uint32_t ref, co
 // template parameter so that the rows are defined and consumed inside one straight-line region: a run-time flag tested
 // twice makes them conditionally defined, and the register allocator then keeps all of them alive around the whole
 // traversal loop (24 registers).
+// dlen (f32 mode only): |d|^2 - 1 as the host measured it on the f64 ray it handed in (rtc_trace_closest), 0 inside the render
+// loop, where the f32 mode re-normalises every bounce direction.
 template <typename R, bool WITH_NORMAL, bool FORCE, bool XF>
-__device__ __forceinline__ int sphere_hits(const DXform<R>* x, const V4<R>& A, const V3<R>& o, const V3<R>& d, Cand<R>* out) {
+__device__ __forceinline__ int sphere_hits(const DXform<R>* x, const V4<R>& A, const V3<R>& o, const V3<R>& d, Cand<R>* out, R dlen) {
   V3<R> C = xyz(A);
   R radius = A.w;
   constexpr bool xf = XF;
@@ -386,10 +388,14 @@ __device__ __forceinline__ int sphere_hits(const DXform<R>* x, const V4<R>& A, c
     t_far = (b + radix) / 2;                      // :89
     t_close = (b - radix) / 2;                    // :90
   } else {
-    // f32: same roots, better-conditioned algebra (perpendicular-distance discriminant, c/q for the small root)
+    // f32: same roots, better-conditioned algebra (perpendicular-distance discriminant, c/q for the small root). The
+    // reference's quadratic assumes |od| = 1 (Sphere.cs:80-90) although its bounce directions are only re-normalised every
+    // third bounce (Raytracer.cs:74-75) and drift up to 1e-5 off unit length in between: its discriminant is bp^2 - c, while
+    // r^2 - |l|^2 = bp^2 (2 - |od|^2) - c. The dlen term restores the reference's value for such a ray (it moves t by 1e-4
+    // on small distant spheres). dlen comes from the f64 ray: the f32 components cannot tell a defect from their own rounding.
     R bp = -dot3(off, od);
     V3<R> l = mk3(rfma(bp, od.x, off.x), rfma(bp, od.y, off.y), rfma(bp, od.z, off.z));
-    R disc = radius * radius - dot3(l, l);
+    R disc = rfma(bp * bp, XF ? R(0) : dlen, radius * radius - dot3(l, l));
     if (FORCE) disc = fmaxf(disc, R(0));  // an accepted grazing hit keeps a real root
     R c = dot3(off, off) - radius * radius;
     R sq = xsqrt(disc);  // NaN when the ray misses
@@ -509,13 +515,13 @@ __device__ __forceinline__ uint32_t ref_of(const PrimRec<R>& p) { return code_of
 
 template <typename R, bool WITH_NORMAL, bool FORCE = false>
 __device__ __forceinline__ int prim_hits(const SceneView<R>& sc, uint32_t ref, const PrimRec<R>& p, const V3<R>& o, const V3<R>& d,
-                                         Cand<R>* out, bool forced_inside = false) {
+                                         Cand<R>* out, bool forced_inside = false, R dlen = R(0)) {
   const int kind = (ref >> REF_KIND_SHIFT) & 3;
   if (kind == DK_TRI) return tri_hits<R, WITH_NORMAL, FORCE>(sc, ref, p.a, p.b, p.c, o, d, out, forced_inside);
   if (kind == DK_PLANE) return plane_hits<R, WITH_NORMAL, FORCE>(p.a, o, d, out);
   if (kind == DK_XSPHERE)
-    return sphere_hits<R, WITH_NORMAL, FORCE, true>(sc.xforms + sc.aux[ref & REF_SLOT_MASK], p.a, o, d, out);
-  return sphere_hits<R, WITH_NORMAL, FORCE, false>(nullptr, p.a, o, d, out);
+    return sphere_hits<R, WITH_NORMAL, FORCE, true>(sc.xforms + sc.aux[ref & REF_SLOT_MASK], p.a, o, d, out, R(0));
+  return sphere_hits<R, WITH_NORMAL, FORCE, false>(nullptr, p.a, o, d, out, dlen);
 }
 
 // The skip hit (previous bounce's Hit) as the trace kernel sees it: primitive slot and inside flag live in
@@ -667,16 +673,18 @@ __device__ __forceinline__ bool consider_cand(const SceneView<R>& sc, uint32_t r
   if (take) {
     best.t = t;
     best.near_ = leaf_near;
-    best.code = slot | (inside ? HIT_INSIDE : 0u) | (which ? HIT_SECOND : 0u);
+    // slot | kind (ref bits 29-30 -> 26-27) | Primitive.Invert (ref bit 26 -> 28) | which | inside
+    best.code = slot | ((ref >> (REF_KIND_SHIFT - HIT_KIND_SHIFT)) & (3u << HIT_KIND_SHIFT)) | ((ref & REF_INVERT) << 2) |
+                (inside ? HIT_INSIDE : 0u) | (which ? HIT_SECOND : 0u);
   }
   return true;
 }
 
 template <typename R>
 __device__ __forceinline__ void test_leaf(const SceneView<R>& sc, uint32_t ref, const PrimRec<R>& pr, R leaf_near, const V3<R>& o,
-                                          const V3<R>& d, const Skip<R>& sk, const SkipSrc<R>& src, uint32_t path, Best<R>& best) {
+                                          const V3<R>& d, R dlen, const Skip<R>& sk, const SkipSrc<R>& src, uint32_t path, Best<R>& best) {
   Cand<R> c[2];  // indexed with constants only: stays in registers
-  const int n = prim_hits<R, false>(sc, ref, pr, o, d, c);
+  const int n = prim_hits<R, false>(sc, ref, pr, o, d, c, false, dlen);
   bool accepted = false;
   if (n > 0) accepted = consider_cand<R>(sc, ref, 0, c[0].inside, c[0].t, c[0].pos, leaf_near, o, d, sk, src, path, best);
   if (n > 1 && !accepted) consider_cand<R>(sc, ref, 1, c[1].inside, c[1].t, c[1].pos, leaf_near, o, d, sk, src, path, best);  // :68-70
@@ -685,7 +693,7 @@ __device__ __forceinline__ void test_leaf(const SceneView<R>& sc, uint32_t ref, 
 // Completes a trace result (distance, slot, inside, which) into the full Hit record (Hit.cs:14-20) by re-evaluating the
 // winning primitive once. Runs in the streaming kernels (k_shade, k_export_hits), not in the traversal loop.
 template <typename R>
-__device__ __forceinline__ void finalize_hit(const SceneView<R>& sc, uint32_t code, const V3<R>& o, const V3<R>& d, V3<R>& pos,
+__device__ __forceinline__ void finalize_hit(const SceneView<R>& sc, uint32_t code, const V3<R>& o, const V3<R>& d, R dlen, V3<R>& pos,
                                              V3<R>& normal, R& t) {
   const PrimRec<R> pr = load_prim(sc, code & REF_SLOT_MASK);
   const uint32_t ref = ref_of(pr);
@@ -695,7 +703,7 @@ __device__ __forceinline__ void finalize_hit(const SceneView<R>& sc, uint32_t co
   Cand<R> c[2];
   c[0].t = c[1].t = Num<R>::nan();
   c[0].pos = c[1].pos = c[0].normal = c[1].normal = mk3(Num<R>::nan(), Num<R>::nan(), Num<R>::nan());
-  prim_hits<R, true, true>(sc, ref, pr, o, d, c, raw_inside);
+  prim_hits<R, true, true>(sc, ref, pr, o, d, c, raw_inside, dlen);
   // forced sphere records are [near (outside), far (inside)]; the other kinds have one record
   const bool second = (kind == DK_SPHERE || kind == DK_XSPHERE) ? raw_inside : false;
   pos = second ? c[1].pos : c[0].pos;
@@ -809,12 +817,12 @@ __global__ void __launch_bounds__(kStreamThreads) k_raygen(CameraView<R> cam, Pa
   V3<R> o, d;
   get_camera_ray(cam, par, x, y, sample, o, d);
   d = normalize3(d);  // Ray.Directional at i == 0
+  R w;
+  set_code(w, HIT_MISS);  // no skip hit
   st4(&pv.dir[path], d.x, d.y, d.z, R(0));
   st4(&pv.tint[path], R(1), R(1), R(1), R(0));
-  st4(&pv.hpos[1][path], o.x, o.y, o.z, R(0));
-  R w;
-  set_code(w, HIT_MISS);
-  st4(&pv.hnrm[1][path], R(0), R(0), R(0), w);
+  st4(&pv.hpos[path], o.x, o.y, o.z, Num<R>::is_f64 ? R(0) : w);
+  if (Num<R>::is_f64) st4(&pv.hnrm[path], R(0), R(0), R(0), w);
 }
 
 template <typename R>
@@ -832,12 +840,11 @@ __global__ void __launch_bounds__(kStreamThreads) k_camera_rays(CameraView<R> ca
 // bank operand) instead of a value selected on the device that would occupy registers for the whole traversal.
 template <typename R>
 struct TraceIO {
-  const V4<R>* dir;       // [path] ray direction
-  const V4<R>* in_hpos;   // [path] xyz = ray origin = previous hit position, w = previous Hit.Distance
+  const V4<R>* dir;       // [path] ray direction (w, f32 mode: its norm defect)
+  const V4<R>* in_hpos;   // [path] xyz = ray origin = previous hit position, w = f64: previous Hit.Distance, f32: the skip hit's code
   const V4<R>* in_hnrm;   // [path] xyz = previous hit normal, w = previous hit code (the skip hit)
   const V4<R>* skip_pos;  // [path] explicit skip position (rtc_trace_closest) or nullptr
-  V4<R>* out_hpos;        // [path] w = Hit.Distance
-  V4<R>* out_hnrm;        // [path] w = hit code
+  THit<R>* out;           // [path] the answer: Hit.Distance, hit code
   const uint32_t* queue;  // live path ids, or nullptr for the identity queue (bounce 0)
   const uint32_t* count;  // number of queue entries
   Control* ctl;
@@ -849,9 +856,9 @@ template <typename R>
 struct ShadeIO {
   V4<R>* dir;             // [path] in: ray direction, out: next direction
   V4<R>* tint;            // [path] throughput
-  const V4<R>* org;       // [path] xyz = this bounce's ray origin (the previous hit record)
-  V4<R>* hpos;            // [path] this bounce's hit: in w = Hit.Distance, out xyz = position
-  V4<R>* hnrm;            // [path] in w = hit code, out xyz = normal
+  const THit<R>* thit;    // [path] this bounce's trace result
+  V4<R>* hpos;            // [path] in: xyz = this bounce's ray origin; out: the hit position (| Hit.Distance or code)
+  V4<R>* hnrm;            // [path] out: the hit normal | code
   V4<R>* radiance;        // [path] out for finished paths
   const uint32_t* queue;  // live path ids of this bounce, or nullptr for the identity queue (bounce 0)
   const uint32_t* count;  // their number
@@ -960,12 +967,13 @@ __global__ void __launch_bounds__(kTraceThreads, 2) k_trace(SceneView<R> sc, Tra
   for (;;) {
     const unsigned m_idle = __ballot_sync(0xFFFFFFFFu, !active);
     if (m_idle == 0xFFFFFFFFu || (!exhausted && __popc(m_idle) > 32 - kRefill)) {
-      // ---- refill ------------------------------------------------------------------------------------------
-      if (finished) {  // (distance, slot | inside | which): position and normal are completed by finalize_hit in k_shade
-        R w;
-        set_code(w, best.code);
-        st4(&io.out_hpos[path], R(0), R(0), R(0), best.t);
-        st4(&io.out_hnrm[path], R(0), R(0), R(0), w);
+      // ---- refill (f64) ------------------------------------------------------------------------------------
+      if (finished) {  // (distance, hit code): position and normal are completed by k_shade / k_export_hits
+        THit<R> th;
+        th.t = best.t;
+        th.code = best.code;
+        th.pad = 0;
+        io.out[path] = th;
         finished = false;
       }
       if (exhausted) {
@@ -1050,7 +1058,7 @@ __global__ void __launch_bounds__(kTraceThreads, 2) k_trace(SceneView<R> sc, Tra
       // ---- leaf step ---------------------------------------------------------------------------------------
       if (active && (cur & REF_LEAF)) {
         if (COUNT) n_prims++;
-        test_leaf<R>(sc, cur, load_prim(sc, cur & REF_SLOT_MASK), cur_near, o, d, sk, src, path, best);
+        test_leaf<R>(sc, cur, load_prim(sc, cur & REF_SLOT_MASK), cur_near, o, d, R(0), sk, src, path, best);
         stack_pop<R>(stk, sp, best.t, cur, cur_near);
       }
     }
@@ -1125,7 +1133,7 @@ __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
 #else
 #define RTC_Q8_BOUNDS __launch_bounds__(kTraceThreads, kTraceMinBlocks)
 #endif
-constexpr int kQ8StateWords = 11;  // per-thread cold state after the stack: d.xyz, path, skip code, o.xyz, inv.xyz
+constexpr int kQ8StateWords = 12;  // per-thread cold state after the stack: d.xyz, path, skip code, o.xyz, inv.xyz, norm defect
 
 template <bool COUNT>
 __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io) {
@@ -1135,7 +1143,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
   // this thread's stack column; its state columns start at sm + state_off
   const uint32_t sm = (uint32_t)__cvta_generic_to_shared(s_stack) + threadIdx.x * 8u;
   const uint32_t st = sm + (uint32_t)sc.q_stack * kStackStride - threadIdx.x * 4u;  // byte address of state word 0
-  enum { S_DX = 0, S_DY, S_DZ, S_PATH, S_SKIP, S_OX, S_OY, S_OZ, S_IX, S_IY, S_IZ };
+  enum { S_DX = 0, S_DY, S_DZ, S_PATH, S_SKIP, S_OX, S_OY, S_OZ, S_IX, S_IY, S_IZ, S_DL };
   const uint32_t count = *io.count;
   uint32_t n_nodes = 0, n_prims = 0, n_node_steps = 0, n_leaf_steps = 0;
   // lane state in `sp`: >= 0 traversing (= stack depth), kFinished = result not written yet, kEmpty = no ray
@@ -1163,12 +1171,12 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
     if (m_idle == 0xFFFFFFFFu || (!exhausted && __popc(m_idle) > 32 - kRefill)) {
       // ---- refill ------------------------------------------------------------------------------------------
       lanes_changed = 1;  // recount after the refill (and keep coming back here once the queue is exhausted)
-      if (sp == kFinished) {  // (distance, slot | inside | which): position and normal are completed by finalize_hit in k_shade
-        R w;
-        set_code(w, best.code);
+      if (sp == kFinished) {  // (distance, hit code) in one 8-byte store: position and normal are completed by k_shade
         const uint32_t fpath = lds32(st + S_PATH * kCol);
-        st4(&io.out_hpos[fpath], R(0), R(0), R(0), best.t);
-        st4(&io.out_hnrm[fpath], R(0), R(0), R(0), w);
+        THit<R> th;
+        th.t = best.t;
+        th.code = best.code;
+        io.out[fpath] = th;
         sp = kEmpty;
       }
       if (exhausted) {
@@ -1186,11 +1194,12 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         got = idx < count;
         if (got) {
           const uint32_t npath = io.queue ? io.queue[idx] : idx;
-          V4<R> dv = ld4(&io.dir[npath]);
-          V4<R> op = ld4(&io.in_hpos[npath]);
-          const uint32_t code = code_of(io.in_hnrm[npath].w);
+          V4<R> dv = ld4(&io.dir[npath]);      // direction | norm defect
+          V4<R> op = ld4(&io.in_hpos[npath]);  // origin | skip code: the whole ray in two 16-byte loads
+          const uint32_t code = code_of(op.w);
           const V3<R> o = xyz(op), d = xyz(dv);
           const V3<R> inv = mk3(clamped_rcp(d.x), clamped_rcp(d.y), clamped_rcp(d.z));
+          sts32(st + S_DL * kCol, __float_as_uint(dv.w));
           sts32(st + S_DX * kCol, __float_as_uint(d.x));
           sts32(st + S_DY * kCol, __float_as_uint(d.y));
           sts32(st + S_DZ * kCol, __float_as_uint(d.z));
@@ -1217,7 +1226,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
           for (int i = 0; finite && i < sc.n_unbounded; i++) {
             if (COUNT) n_prims++;
             const uint32_t uref = sc.unbounded[i];
-            test_leaf<R>(sc, uref, load_prim(sc, uref & REF_SLOT_MASK), -Num<R>::inf(), o, d, sk, src, npath, best);
+            test_leaf<R>(sc, uref, load_prim(sc, uref & REF_SLOT_MASK), -Num<R>::inf(), o, d, dv.w, sk, src, npath, best);
           }
           // virtual root group: one inner child in slot 0 = node 0
           igx = 0;
@@ -1325,7 +1334,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
                             __uint_as_float(lds32(st + S_OZ * kCol)));
         const V3<R> d = mk3(__uint_as_float(lds32(st + S_DX * kCol)), __uint_as_float(lds32(st + S_DY * kCol)),
                             __uint_as_float(lds32(st + S_DZ * kCol)));
-        test_leaf<R>(sc, ref_of(pr), pr, R(0), o, d, sk, src, lds32(st + S_PATH * kCol), best);
+        test_leaf<R>(sc, ref_of(pr), pr, R(0), o, d, __uint_as_float(lds32(st + S_DL * kCol)), sk, src, lds32(st + S_PATH * kCol), best);
       }
     }
     bool done_now = false;
@@ -1356,13 +1365,153 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
 template <typename R>
 __device__ __forceinline__ R luminance(R r, R g, R b) { return (R(0.299) * r + R(0.587) * g) + R(0.114) * b; }
 
+// ---------------------------------------------------------------------------------------------------------
+// Shading arithmetic of the f32 mode. Like the traversal (xrcp / xsqrt above), k_shade<float> contains no call: IEEE
+// division, sqrtf, powf, acosf and sincosf all carry out-of-line slow paths whose calling convention costs registers
+// around the whole kernel (80 -> 56 registers without them). Everything here is accurate to a few f32 ulp, three orders
+// below the 1 % image tolerance; the f64 mode keeps the exact libm forms of the reference.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float xlog2(float a) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float xexp2(float a) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float xrsqrt(float a) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+// RandomShine's polar cosine z = u^(1/shininess) (Raytracer.cs:53) together with sqrt(1 - z^2), which CreateHorizon needs
+// (Vec4D.cs:56). For mirror-like shininess (1e5, 1e6) z is within 1e-5 of 1 and 1 - z^2 computed from a rounded z has no
+// significant bits left in f32, so the complement w = 1 - z is carried instead: for a small exponent e = ln(u) / shininess,
+// w = -expm1(e) by its series, and 1 - z^2 = w (2 - w).
+__device__ __forceinline__ void shine_polar(float u, float shininess, float& z, float& sn) {
+  const float x = xlog2(u) * xrcp(shininess);  // log2 of the result; u = 0 gives -inf -> z = 0 like pow(0, p)
+  const float e = x * 0.6931471805599453f;
+  float w;
+  if (fabsf(e) < 0.25f) {
+    w = -e * fmaf(e, fmaf(e, fmaf(e, fmaf(e, fmaf(e, 1.0f / 720.0f, 1.0f / 120.0f), 1.0f / 24.0f), 1.0f / 6.0f), 0.5f), 1.0f);
+    z = 1.0f - w;
+  } else {
+    z = xexp2(x);
+    w = 1.0f - z;
+  }
+  sn = xsqrt(w * (2.0f - w));  // NaN for z > 1 (negative shininess), like the reference's sqrt(1 - z^2)
+}
+// acos on [0, 1) (the diffuse lobe's 2 acos(u) / pi, Raytracer.cs:215): sqrt(1 - x) * p(x), Abramowitz & Stegun 4.4.46,
+// |error| <= 2e-8.
+__device__ __forceinline__ float xacos01(float x) {
+  float p = fmaf(x, -0.0012624911f, 0.0066700901f);
+  p = fmaf(x, p, -0.0170881256f);
+  p = fmaf(x, p, 0.0308918810f);
+  p = fmaf(x, p, -0.0501743046f);
+  p = fmaf(x, p, 0.0889789874f);
+  p = fmaf(x, p, -0.2145988016f);
+  p = fmaf(x, p, 1.5707963050f);
+  return xsqrt(1.0f - x) * p;
+}
+
+// CreateHorizon with the polar sine handed in (f32 mode): same construction as create_horizon above, approximate rsqrt /
+// sin / cos (angle = 2 pi u, u in [0, 1): one MUFU each after the range scaling the instruction does itself).
+__device__ __forceinline__ V3<float> create_horizon_f32(const V3<float>& pole, float z, float sn, float u_theta) {
+  V3<float> c = mk3(pole.y, -pole.x, 0.0f);  // pole x (0, 0, 1)
+  const float l2 = c.x * c.x + c.y * c.y;
+  if (l2 == 0.0f) {
+    c = mk3(1.0f, 0.0f, 0.0f);
+  } else {
+    const float il = xrsqrt(l2);
+    c = mk3(c.x * il, c.y * il, 0.0f);
+  }
+  const float theta = u_theta * 6.283185307179586f;
+  const float s = __sinf(theta), co = __cosf(theta);
+  const float cosOpp = 1.0f - co;
+  const V3<float> v = (pole * z) + (c * sn);
+  const V3<float>& a = pole;
+  const float m00 = co + a.x * a.x * cosOpp, m01 = a.x * a.y * cosOpp - a.z * s, m02 = a.x * a.z * cosOpp + a.y * s;
+  const float m10 = a.y * a.x * cosOpp + a.z * s, m11 = co + a.y * a.y * cosOpp, m12 = a.y * a.z * cosOpp - a.x * s;
+  const float m20 = a.z * a.x * cosOpp - a.y * s, m21 = a.z * a.y * cosOpp + a.x * s, m22 = co + a.z * a.z * cosOpp;
+  return mk3((m00 * v.x + m01 * v.y) + m02 * v.z, (m10 * v.x + m11 * v.y) + m12 * v.z, (m20 * v.x + m21 * v.y) + m22 * v.z);
+}
+
+// The material of one slot: colours, ior, shininess (Primitive.cs:16-129; Specular / Refraction already black when the
+// primitive is not reflective). f64: four 32-byte vectors; f32: one 256-bit load of 12 halfs + 2 floats.
+template <typename R>
+struct Mat {
+  V3<R> emis, diff, spec, refr;
+  R ior, shininess;
+};
+__device__ __forceinline__ void unpack_half2(uint32_t w, float& lo, float& hi) {
+  asm("{.reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h;}" : "=f"(lo), "=f"(hi) : "r"(w));
+}
+__device__ __forceinline__ Mat<float> load_mat(const DMat<float>* mp) {
+  uint32_t w[8];
+  ldg256(mp, w);
+  Mat<float> m;
+  unpack_half2(w[0], m.emis.x, m.emis.y);
+  unpack_half2(w[1], m.emis.z, m.diff.x);
+  unpack_half2(w[2], m.diff.y, m.diff.z);
+  unpack_half2(w[3], m.spec.x, m.spec.y);
+  unpack_half2(w[4], m.spec.z, m.refr.x);
+  unpack_half2(w[5], m.refr.y, m.refr.z);
+  m.ior = __uint_as_float(w[6]);
+  m.shininess = __uint_as_float(w[7]);
+  return m;
+}
+__device__ __forceinline__ Mat<double> load_mat(const DMat<double>* mp) {
+  const V4<double> e = ldg4(&mp->emis_ior), d = ldg4(&mp->diff_shin), sp = ldg4(&mp->spec), rf = ldg4(&mp->refr);
+  Mat<double> m;
+  m.emis = xyz(e);
+  m.diff = xyz(d);
+  m.spec = xyz(sp);
+  m.refr = xyz(rf);
+  m.ior = e.w;
+  m.shininess = d.w;
+  return m;
+}
+
+// Completes the trace kernel's answer (distance, code) into position and normal of the Hit (Hit.cs:14-20). f32 mode: flat
+// triangles and plain spheres -- all of BASELINE's synthetic scenes -- need only the 16-byte sgeom record: the position is
+// origin + t * direction (Sphere.cs:94,97 compute exactly that; for a triangle it equals Triangle.cs:130's v0 + u e1 + v e2
+// to f32 rounding), the normal is +-N or +-(P - C) / r by the primitive's own inside flag. Planes, transformed spheres and
+// vertex-normal triangles, and everything in f64 mode, re-evaluate the primitive (finalize_hit).
+template <typename R>
+__device__ __forceinline__ void complete_hit(const SceneView<R>& sc, uint32_t code, const V3<R>& o, const V3<R>& d, R dlen, R t_in,
+                                             V3<R>& pos, V3<R>& normal, R& t) {
+  if constexpr (!Num<R>::is_f64) {
+    const uint32_t kind = (code >> HIT_KIND_SHIFT) & 3u;
+    const bool raw_inside = (((code >> 30) ^ (code >> 28)) & 1u) != 0;
+    if (kind == DK_TRI || kind == DK_SPHERE) {
+      const V4<R> sg = ldg4(&sc.sgeom[code & REF_SLOT_MASK]);
+      if (kind == DK_SPHERE || code_of(sg.w) == 0u) {
+        t = t_in;
+        pos = mk3(rfma(t_in, d.x, o.x), rfma(t_in, d.y, o.y), rfma(t_in, d.z, o.z));
+        V3<R> n = xyz(sg);
+        if (kind == DK_SPHERE) {
+          const R ir = xrcp(sg.w);
+          n = mk3((pos.x - sg.x) * ir, (pos.y - sg.y) * ir, (pos.z - sg.z) * ir);
+        }
+        normal = raw_inside ? neg3(n) : n;
+        return;
+      }
+    }
+  }
+  finalize_hit<R>(sc, code, o, d, dlen, pos, normal, t);
+}
+
 // shade: one bounce of Raytracer.GetColor (Raytracing/Raytracer.cs:71-245) for every live path: terminal tests,
 // RandomShine, Fresnel / total internal reflection, lobe roulette, next ray, tint. Terminated paths write their
-// radiance; the survivors overwrite dir/tint in place and are appended to the next bounce's queue by a warp-aggregated
-// stream compaction (ballot + popc + one atomicAdd per warp) -- the loop's `break`/`return` of the reference.
+// radiance; the survivors overwrite their ray (hpos = origin, dir) and tint in place and are appended to the next bounce's
+// queue by a warp-aggregated stream compaction (ballot + popc + one atomicAdd per warp) -- the loop's `break`/`return` of
+// the reference.
 template <typename R>
 __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(SceneView<R> sc, ParamsView<R> par, Band band, ShadeIO<R> io,
                                                            int bounce) {
+  constexpr bool F64 = Num<R>::is_f64;
   const uint32_t count = *io.count;
   const uint32_t* queue = io.queue;
   uint32_t* qout = io.queue_out;
@@ -1376,30 +1525,8 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
     uint32_t path = 0;
     if (idx < count) {
     path = identity_queue ? idx : queue[idx];
-    V4<R> hp = ld4(&io.hpos[path]);
-    V4<R> hn = ld4(&io.hnrm[path]);
-    const uint32_t code = code_of(hn.w);
-    // every load that depends on (path, slot) only is issued up front, behind one another: the kernel is bound by gather
-    // latency, not by arithmetic
-    V4<R> m_emis, m_diff, m_spec, m_refr, tv, dv;
-    if (code != HIT_MISS) {  // complete the Hit record: it is also the next ray's origin and skip hit
-      const DMat<R>* mp = sc.mats + (code & REF_SLOT_MASK);
-      V3<R> ro = xyz(ld4(&io.org[path]));
-      dv = ld4(&io.dir[path]);
-      m_emis = ldg4(&mp->emis_ior);
-      m_diff = ldg4(&mp->diff_shin);
-      m_spec = ldg4(&mp->spec);
-      m_refr = ldg4(&mp->refr);
-      tv = ld4(&io.tint[path]);
-      V3<R> rd = xyz(dv);
-      V3<R> fp, fn;
-      R ft;
-      finalize_hit<R>(sc, code, ro, rd, fp, fn, ft);
-      hp.x = fp.x; hp.y = fp.y; hp.z = fp.z; hp.w = ft;
-      hn.x = fn.x; hn.y = fn.y; hn.z = fn.z;
-      st4(&io.hpos[path], hp.x, hp.y, hp.z, hp.w);
-      st4(&io.hnrm[path], hn.x, hn.y, hn.z, hn.w);
-    }
+    const THit<R> th = io.thit[path];
+    const uint32_t code = th.code;
     bool done = false;
     R out_r = 0, out_g = 0, out_b = 0;
     int dbg = 0;  // BounceType.Skipped
@@ -1415,57 +1542,71 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
       }
       done = true;
     } else {
+      // every load that depends on (path, slot) only is issued up front, behind one another: the kernel is bound by gather
+      // latency, not by arithmetic
+      const V4<R> op = ld4(&io.hpos[path]);
+      const V4<R> dv = ld4(&io.dir[path]);
+      const V4<R> tv = ld4(&io.tint[path]);
+      const Mat<R> m = load_mat(sc.mats + (code & REF_SLOT_MASK));
+      const V3<R> d = xyz(dv);
+      V3<R> pos, normal;
+      R hit_t;
+      complete_hit<R>(sc, code, xyz(op), d, F64 ? R(0) : dv.w, th.t, pos, normal, hit_t);  // also the next ray's origin and skip hit
       const bool hit_inside = (code & HIT_INSIDE) != 0;
+      bool have_out = false;
+      V3<R> out_dir = mk3(R(0), R(0), R(0));
+      R nt_r = 0, nt_g = 0, nt_b = 0, total_l = 0;
 
       if (par.debug_geom) {  // :93-98
         dbg = 9;
-        out_r = (m_spec.x + m_diff.x) + m_emis.x;
-        out_g = (m_spec.y + m_diff.y) + m_emis.y;
-        out_b = (m_spec.z + m_diff.z) + m_emis.z;
+        out_r = (m.spec.x + m.diff.x) + m.emis.x;
+        out_g = (m.spec.y + m.diff.y) + m.emis.y;
+        out_b = (m.spec.z + m.diff.z) + m.emis.z;
         done = true;
       } else if (bounce >= par.recursion) {  // :100-104
         dbg = 7;
-        out_r = tv.x * m_emis.x;
-        out_g = tv.y * m_emis.y;
-        out_b = tv.z * m_emis.z;
-        done = true;
       } else {
         int x, y;
         uint32_t sample;
         band_pixel(band, path, x, y, sample);
         const uint32_t pixel = (uint32_t)(y * par.width + x);
         const uint32_t stage = 1u + (uint32_t)bounce;
-        V3<R> d = xyz(dv), normal = xyz(hn);
-        const R shininess = m_diff.w, ior = m_emis.w;
         R u1, u2;
         uniforms2<R>(par.seed_lo, par.seed_hi, pixel, sample, stage, 0, u1, u2);
         // RandomShine, :51-56
-        R zs = (shininess == Num<R>::inf()) ? R(1) : rpow(u1, 1 / shininess);
-        R theta_s = u2 * R(3.14159265358979323846) * 2;
-        V3<R> rough = create_horizon(normal, zs, theta_s);  // :108
-        R diff_l = luminance(m_diff.x, m_diff.y, m_diff.z), spec_l = luminance(m_spec.x, m_spec.y, m_spec.z),
-          refr_l = luminance(m_refr.x, m_refr.y, m_refr.z), emis_l = luminance(m_emis.x, m_emis.y, m_emis.z);  // :110-113
+        V3<R> rough;
+        if constexpr (F64) {
+          R zs = (m.shininess == Num<R>::inf()) ? R(1) : rpow(u1, 1 / m.shininess);
+          rough = create_horizon(normal, zs, u2 * R(3.14159265358979323846) * 2);  // :108
+        } else {
+          float zs = 1.0f, sn = 0.0f;
+          if (m.shininess != Num<R>::inf()) shine_polar(u1, m.shininess, zs, sn);
+          rough = create_horizon_f32(normal, zs, sn, u2);
+        }
+        R diff_l = luminance(m.diff.x, m.diff.y, m.diff.z), spec_l = luminance(m.spec.x, m.spec.y, m.spec.z),
+          refr_l = luminance(m.refr.x, m.refr.y, m.refr.z), emis_l = luminance(m.emis.x, m.emis.y, m.emis.z);  // :110-113
         R cosv = -dot3(rough, d);  // :115
         R cos_out = 0, ior_ratio = 0;
-        if (((refr_l > 0) | (spec_l > 0)) && ior != 0 && cosv >= 0) {  // :120
+        if (((refr_l > 0) | (spec_l > 0)) && m.ior != 0 && cosv >= 0) {  // :120
           R ior_in, ior_out;
           if (hit_inside) {
-            ior_in = ior;
+            ior_in = m.ior;
             ior_out = par.air_ior;
           } else {
             ior_in = par.air_ior;
-            ior_out = ior;
+            ior_out = m.ior;
           }
-          ior_ratio = ior_in / ior_out;                              // :136
-          R sin_out = ior_ratio * rsqrt_(1 - (cosv * cosv));         // :137
-          if (sin_out >= 1) {                                        // :140-145
+          ior_ratio = F64 ? ior_in / ior_out : xdiv(ior_in, ior_out);   // :136
+          R sin_out = ior_ratio * xsqrt(1 - (cosv * cosv));             // :137
+          if (sin_out >= 1) {                                           // :140-145
             refr_l = 0;
             dbg_f = 1;
           } else {
-            cos_out = rsqrt_(1 - (sin_out * sin_out));               // :148
-            R rs = ((ior_out * cosv) - (ior_in * cos_out)) / ((ior_out * cosv) + (ior_in * cos_out));  // :149
-            R rp = ((ior_in * cosv) - (ior_out * cos_out)) / ((ior_in * cosv) + (ior_out * cos_out));  // :150
-            R ratio = ((rs * rs) + (rp * rp)) / 2;                   // :151
+            cos_out = xsqrt(1 - (sin_out * sin_out));                   // :148
+            const R rs_n = (ior_out * cosv) - (ior_in * cos_out), rs_d = (ior_out * cosv) + (ior_in * cos_out);  // :149
+            const R rp_n = (ior_in * cosv) - (ior_out * cos_out), rp_d = (ior_in * cosv) + (ior_out * cos_out);  // :150
+            const R rs = F64 ? rs_n / rs_d : xdiv(rs_n, rs_d), rp = F64 ? rp_n / rp_d : xdiv(rp_n, rp_d);
+            R ratio = ((rs * rs) + (rp * rp)) * R(0.5);                 // :151 (x / 2 == x * 0.5 exactly)
             spec_l *= ratio;
             refr_l *= 1 - ratio;
             dbg_f = ratio;
@@ -1473,10 +1614,7 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
         } else {
           refr_l = 0;  // :158-161
         }
-        R total_l = ((diff_l + spec_l) + refr_l) + emis_l;  // :163
-        bool have_out = false;
-        V3<R> out_dir = mk3(R(0), R(0), R(0));
-        R nt_r = 0, nt_g = 0, nt_b = 0;
+        total_l = ((diff_l + spec_l) + refr_l) + emis_l;  // :163
         if (total_l <= 0) {  // :165-169
           dbg = 6;
         } else {
@@ -1490,7 +1628,7 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
             if (hit_inside) {
               nt_r = nt_g = nt_b = 1;
             } else {
-              nt_r = m_refr.x; nt_g = m_refr.y; nt_b = m_refr.z;
+              nt_r = m.refr.x; nt_g = m.refr.y; nt_b = m.refr.z;
             }
           } else if (spec_l != 0 && (ray_rand -= spec_l) <= 0) {  // :194-209
             dbg = 3;
@@ -1499,36 +1637,53 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
               dbg = 2;
               out_dir = od;
               have_out = true;
-              nt_r = m_spec.x; nt_g = m_spec.y; nt_b = m_spec.z;
+              nt_r = m.spec.x; nt_g = m.spec.y; nt_b = m.spec.z;
             }
           } else if (diff_l != 0 && (ray_rand -= diff_l) <= 0) {  // :210-219
             dbg = 1;
             R u5, u6;
             uniforms2<R>(par.seed_lo, par.seed_hi, pixel, sample, stage, 2, u5, u6);
-            R z = (2 * racos(u4)) / R(3.14159265358979323846);
-            R theta = u5 * R(3.14159265358979323846) * 2;
-            out_dir = create_horizon(normal, z, theta);
+            if constexpr (F64) {
+              R z = (2 * racos(u4)) / R(3.14159265358979323846);
+              out_dir = create_horizon(normal, z, u5 * R(3.14159265358979323846) * 2);
+            } else {
+              const float z = xacos01(u4) * 0.6366197723675814f;  // 2 acos(u) / pi
+              out_dir = create_horizon_f32(normal, z, xsqrt(1.0f - z * z), u5);
+            }
             have_out = true;
-            nt_r = m_diff.x; nt_g = m_diff.y; nt_b = m_diff.z;
+            nt_r = m.diff.x; nt_g = m.diff.y; nt_b = m.diff.z;
           } else {
             dbg = 5;  // :220-229 emission picked
           }
           // :231-232 `outRay == Ray.Zero`
-          if (have_out && hp.x == 0 && hp.y == 0 && hp.z == 0 && out_dir.x == 0 && out_dir.y == 0 && out_dir.z == 0)
+          if (have_out && pos.x == 0 && pos.y == 0 && pos.z == 0 && out_dir.x == 0 && out_dir.y == 0 && out_dir.z == 0)
             have_out = false;
         }
-        if (have_out) {
-          R m = risnan(total_l) ? total_l : (total_l > 1 ? total_l : R(1));  // Math.Max(totalLum, 1), :238
-          R tr = tv.x * (nt_r * m), tg = tv.y * (nt_g * m), tb = tv.z * (nt_b * m);  // :238-240
+      }
+      if (have_out) {
+        R mx = risnan(total_l) ? total_l : (total_l > 1 ? total_l : R(1));  // Math.Max(totalLum, 1), :238
+        R tr = tv.x * (nt_r * mx), tg = tv.y * (nt_g * mx), tb = tv.z * (nt_b * mx);  // :238-240
+        if constexpr (F64) {
           if ((bounce + 1) % 3 == 0) out_dir = normalize3(out_dir);  // :74-75 of the next iteration
-          st4(&io.dir[path], out_dir.x, out_dir.y, out_dir.z, R(0));
-          st4(&io.tint[path], tr, tg, tb, R(0));
         } else {
-          out_r = tv.x * m_emis.x;  // :245
-          out_g = tv.y * m_emis.y;
-          out_b = tv.z * m_emis.z;
-          done = true;
+          // f32 mode keeps every ray direction at unit length: the reference's sphere test silently assumes it (Sphere.cs:80-90),
+          // and the drift it tolerates between its every-third-bounce normalisations is far below f32 resolution anyway
+          const float il = xrsqrt((out_dir.x * out_dir.x + out_dir.y * out_dir.y) + out_dir.z * out_dir.z);
+          out_dir = out_dir * il;
         }
+        st4(&io.dir[path], out_dir.x, out_dir.y, out_dir.z, R(0));
+        st4(&io.tint[path], tr, tg, tb, R(0));
+      } else if (!done) {
+        out_r = tv.x * m.emis.x;  // :245
+        out_g = tv.y * m.emis.y;
+        out_b = tv.z * m.emis.z;
+        done = true;
+      }
+      if (have_out || io.dbg_type) {  // the completed Hit: the next ray's origin and skip hit (and rtc_debug_trace's record)
+        R w;
+        set_code(w, code);
+        st4(&io.hpos[path], pos.x, pos.y, pos.z, F64 ? hit_t : w);
+        st4(&io.hnrm[path], normal.x, normal.y, normal.z, w);
       }
     }
     if (io.dbg_type) {
@@ -1592,7 +1747,7 @@ __global__ void __launch_bounds__(kStreamThreads) k_accumulate(ParamsView<R> par
 template <typename R>
 __global__ void __launch_bounds__(kStreamThreads) k_import_rays(SceneView<R> sc, int64_t n, const rtc_ray* rays,
                                                                  const rtc_hit* skip, const int32_t* id_to_slot,
-                                                                 PathView<R> pv, int prev) {
+                                                                 PathView<R> pv) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
     pv.ctl->count[0] = (uint32_t)n;
@@ -1601,7 +1756,10 @@ __global__ void __launch_bounds__(kStreamThreads) k_import_rays(SceneView<R> sc,
   }
   if (i >= n) return;
   const rtc_ray& r = rays[i];
-  st4(&pv.dir[i], (R)r.dir[0], (R)r.dir[1], (R)r.dir[2], R(0));
+  // f32 mode: how far the f64 direction is off unit length (the reference's sphere test assumes it is not, Sphere.cs:80-90;
+  // sphere_hits needs the defect to land on the reference's roots, and f32 components cannot carry one below 1e-7)
+  const double dl = ((r.dir[0] * r.dir[0] + r.dir[1] * r.dir[1]) + r.dir[2] * r.dir[2]) - 1.0;
+  st4(&pv.dir[i], (R)r.dir[0], (R)r.dir[1], (R)r.dir[2], Num<R>::is_f64 ? R(0) : (R)dl);
   R t = 0, w;
   R nx = 0, ny = 0, nz = 0, px = 0, py = 0, pz = 0;
   uint32_t code = HIT_MISS;
@@ -1613,26 +1771,30 @@ __global__ void __launch_bounds__(kStreamThreads) k_import_rays(SceneView<R> sc,
     px = (R)s.position[0]; py = (R)s.position[1]; pz = (R)s.position[2];
   }
   set_code(w, code);
-  st4(&pv.hpos[prev][i], (R)r.origin[0], (R)r.origin[1], (R)r.origin[2], t);
-  st4(&pv.hnrm[prev][i], nx, ny, nz, w);
+  st4(&pv.hpos[i], (R)r.origin[0], (R)r.origin[1], (R)r.origin[2], Num<R>::is_f64 ? t : w);
+  st4(&pv.hnrm[i], nx, ny, nz, w);
   st4(&pv.skip_pos[i], px, py, pz, R(0));
 }
 
+// finalize != 0: straight after a trace launch (rtc_trace_closest) -- the Hit record is completed here from the ray still in
+// hpos / dir; finalize == 0: after k_shade (rtc_debug_trace), which has already stored position and normal.
 template <typename R>
-__global__ void __launch_bounds__(kStreamThreads) k_export_hits(SceneView<R> sc, int64_t n, PathView<R> pv, int cur, rtc_hit* out,
+__global__ void __launch_bounds__(kStreamThreads) k_export_hits(SceneView<R> sc, int64_t n, PathView<R> pv, rtc_hit* out,
                                                                  int finalize) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  V4<R> hp = ld4(&pv.hpos[cur][i]);
-  V4<R> hn = ld4(&pv.hnrm[cur][i]);
-  uint32_t code = code_of(hn.w);
-  if (finalize && code != HIT_MISS) {  // straight after k_trace; after k_shade the record is already complete
-    V3<R> ro = xyz(ld4(&pv.hpos[cur ^ 1][i])), rd = xyz(ld4(&pv.dir[i]));
-    V3<R> fp, fn;
-    R ft;
-    finalize_hit<R>(sc, code, ro, rd, fp, fn, ft);
-    hp.x = fp.x; hp.y = fp.y; hp.z = fp.z; hp.w = ft;
-    hn.x = fn.x; hn.y = fn.y; hn.z = fn.z;
+  const THit<R> th = pv.thit[i];
+  const uint32_t code = th.code;
+  V4<R> hp = ld4(&pv.hpos[i]);
+  V3<R> fp = xyz(hp), fn = mk3(R(0), R(0), R(0));
+  R ft = th.t;
+  if (code != HIT_MISS) {
+    if (finalize) {
+      const V4<R> dv = ld4(&pv.dir[i]);
+      finalize_hit<R>(sc, code, xyz(hp), xyz(dv), Num<R>::is_f64 ? R(0) : dv.w, fp, fn, ft);
+    } else {
+      fn = xyz(ld4(&pv.hnrm[i]));
+    }
   }
   rtc_hit h;
   if (code == HIT_MISS) {
@@ -1644,9 +1806,9 @@ __global__ void __launch_bounds__(kStreamThreads) k_export_hits(SceneView<R> sc,
   } else {
     h.prim = sc.prim_id[code & REF_SLOT_MASK];
     h.inside = (code & HIT_INSIDE) ? 1 : 0;
-    h.t = (double)hp.w;
-    h.position[0] = (double)hp.x; h.position[1] = (double)hp.y; h.position[2] = (double)hp.z;
-    h.normal[0] = (double)hn.x; h.normal[1] = (double)hn.y; h.normal[2] = (double)hn.z;
+    h.t = (double)ft;
+    h.position[0] = (double)fp.x; h.position[1] = (double)fp.y; h.position[2] = (double)fp.z;
+    h.normal[0] = (double)fn.x; h.normal[1] = (double)fn.y; h.normal[2] = (double)fn.z;
   }
   out[i] = h;
 }
@@ -1680,22 +1842,22 @@ __global__ void __launch_bounds__(kStreamThreads) k_overlay_rays(CameraView<R> c
   V3<R> o, d;
   camera_get_ray(cam, R(x), R(y), o, d);  // camera.GetRay(x, y)
   o = o + (d * cam.image_plane);          // .Offset(camera.imagePlane), DebugRaycaster.cs:236
-  st4(&pv.dir[path], d.x, d.y, d.z, R(0));
-  st4(&pv.hpos[1][path], o.x, o.y, o.z, R(0));
   R w;
   set_code(w, HIT_MISS);
-  st4(&pv.hnrm[1][path], R(0), R(0), R(0), w);
+  st4(&pv.dir[path], d.x, d.y, d.z, R(0));
+  st4(&pv.hpos[path], o.x, o.y, o.z, Num<R>::is_f64 ? R(0) : w);
+  if (Num<R>::is_f64) st4(&pv.hnrm[path], R(0), R(0), R(0), w);
 }
 
 template <typename R>
 __global__ void __launch_bounds__(kStreamThreads) k_overlay_prims(SceneView<R> sc, ParamsView<R> par, Band band, PathView<R> pv,
-                                                                   int cur, int32_t* out) {
+                                                                   int32_t* out) {
   uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= band.n_pix) return;
   int px, py;
   band_pix_xy(band, pix, px, py);
   size_t g = (size_t)py * par.width + px;
-  const uint32_t code = code_of(pv.hnrm[cur][pix].w);
+  const uint32_t code = pv.thit[pix].code;
   out[g] = code == HIT_MISS ? -1 : sc.prim_id[code & REF_SLOT_MASK];
 }
 
@@ -1730,8 +1892,7 @@ cudaError_t Kernels<R>::camera_rays(const LaunchCfg& cfg, const CameraView<R>& c
 }
 
 template <typename R>
-cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, int prev, int cur,
-                              bool identity_queue) {
+cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, bool identity_queue) {
   const size_t smem = Num<R>::is_f64 ? (size_t)sc.q_stack * kTraceThreads * (4 + sizeof(R))
                                      : (size_t)sc.q_stack * kTraceThreads * sizeof(uint2) + kQ8StateWords * kTraceThreads * sizeof(float);
   // resident CTAs per SM for the (device, stack size) last seen (persistent grid = all of them); function attributes are
@@ -1757,11 +1918,10 @@ cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, cons
   int grid = cfg.sm_count * per_sm;
   TraceIO<R> io;
   io.dir = pv.dir;
-  io.in_hpos = pv.hpos[prev];
-  io.in_hnrm = pv.hnrm[prev];
+  io.in_hpos = pv.hpos;
+  io.in_hnrm = pv.hnrm;
   io.skip_pos = pv.skip_pos;
-  io.out_hpos = pv.hpos[cur];
-  io.out_hnrm = pv.hnrm[cur];
+  io.out = pv.thit;
   io.queue = identity_queue ? nullptr : pv.queue[q];
   io.count = &pv.ctl->count[q];
   io.ctl = pv.ctl;
@@ -1781,14 +1941,14 @@ cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, cons
 
 template <typename R>
 cudaError_t Kernels<R>::shade(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,
-                              const PathView<R>& pv, int q, int cur, int bounce, bool identity_queue) {
+                              const PathView<R>& pv, int q, int bounce, bool identity_queue) {
   int grid = cfg.sm_count * 8;
   ShadeIO<R> io;
   io.dir = pv.dir;
   io.tint = pv.tint;
-  io.org = pv.hpos[cur ^ 1];
-  io.hpos = pv.hpos[cur];
-  io.hnrm = pv.hnrm[cur];
+  io.thit = pv.thit;
+  io.hpos = pv.hpos;
+  io.hnrm = pv.hnrm;
   io.radiance = pv.radiance;
   io.queue = identity_queue ? nullptr : pv.queue[q];
   io.count = &pv.ctl->count[q];
@@ -1815,15 +1975,15 @@ cudaError_t Kernels<R>::accumulate(const LaunchCfg& cfg, const ParamsView<R>& pa
 
 template <typename R>
 cudaError_t Kernels<R>::import_rays(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const rtc_ray* rays,
-                                    const rtc_hit* skip, const int32_t* id_to_slot, const PathView<R>& pv, int prev) {
-  k_import_rays<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, n, rays, skip, id_to_slot, pv, prev);
+                                    const rtc_hit* skip, const int32_t* id_to_slot, const PathView<R>& pv) {
+  k_import_rays<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, n, rays, skip, id_to_slot, pv);
   return cudaGetLastError();
 }
 
 template <typename R>
-cudaError_t Kernels<R>::export_hits(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const PathView<R>& pv, int cur,
+cudaError_t Kernels<R>::export_hits(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const PathView<R>& pv,
                                     rtc_hit* out, bool finalize) {
-  k_export_hits<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, n, pv, cur, out, finalize ? 1 : 0);
+  k_export_hits<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, n, pv, out, finalize ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -1836,8 +1996,8 @@ cudaError_t Kernels<R>::overlay_rays(const LaunchCfg& cfg, const CameraView<R>& 
 
 template <typename R>
 cudaError_t Kernels<R>::overlay_prims(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,
-                                      const PathView<R>& pv, int cur, int32_t* out) {
-  k_overlay_prims<R><<<div_up(band.n_pix, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, par, band, pv, cur, out);
+                                      const PathView<R>& pv, int32_t* out) {
+  k_overlay_prims<R><<<div_up(band.n_pix, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(sc, par, band, pv, out);
   return cudaGetLastError();
 }
 

@@ -5,15 +5,19 @@
 //   DNode<R>  f64 mode: 4 children per node (256 B), stored as lo[axis][child] / hi[axis][child] rows + 4 child references,
 //             so two 16-byte loads = one bound of all children. (f32 mode uses the quantised 8-wide CNode below.)
 //   DPrim<R>  3 x V4 per primitive, stored in left-first DFS leaf order so slot == leaf order (tie-break key):
-//               triangle  a=(v0.xyz,N.x) b=(e1.xyz,N.y) c=(e2.xyz,ref)      (Triangle.cs:22-29; N.z lives in prim_nz[])
+//               triangle  a=(v0.xyz,N.x) b=(e1.xyz,N.y) c=(e2.xyz,ref)      (Triangle.cs:22-29; the whole N lives in sgeom[])
 //               sphere    a=(center.xyz,radius)            c=(0,0,0,ref)     (Sphere.cs:11-14)
 //               plane     a=(normal.xyz,originDistance)    c=(0,0,0,ref)     (Plane.cs:13-14)
 //             ref = the leaf reference (REF_LEAF | kind | flags | slot) as raw bits in the w lane, so that a leaf test is
 //             ONE memory round trip (three 16-byte loads issued together) instead of reference -> record.
 //   DXform<R> 9 x V4 for transformed spheres (rows 0-2 of MatrixToWorld, MatrixToObject, MatrixToNormal) or
 //             vertex-normal triangles (n0,n1,n2 in rows 0-2).
-//   DMat<R>   4 x V4: (emission, ior) (diffuse, shininess) (specular, 0) (refraction, 0)  (Primitive.cs:16-129)
-//   path pool: SoA of V4<R> per path: dir, tint, 2 x (hit position|t, hit normal|code) ping-pong, radiance.
+//   DMat<R>   f64: 4 x V4: (emission, ior) (diffuse, shininess) (specular, 0) (refraction, 0)  (Primitive.cs:16-129)
+//             f32: 32 B: the four colours as 12 halfs, then ior and shininess as floats (one 256-bit load)
+//   sgeom     V4<R> per slot, what completing a hit record needs without fetching the 48-byte primitive: triangle (N.xyz,
+//             flag bits: 1 = vertex normals), sphere (centre.xyz, radius), plane (normal.xyz, 0)
+//   path pool: SoA per path: dir (xyz | f32: norm defect), tint, hpos (hit position | f64: Hit.Distance, f32: hit code),
+//             hnrm (hit normal | hit code), thit (the trace kernel's output: distance, code), radiance.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -42,6 +46,9 @@ constexpr uint32_t REF_VNORMALS_AUX = 0x40000000u;  // flag kept in aux[] for ve
 constexpr uint32_t HIT_MISS = 0xFFFFFFFFu;
 constexpr uint32_t HIT_INSIDE = 1u << 30;
 constexpr uint32_t HIT_SECOND = 1u << 29;  // the hit is the second entry of the primitive's Hit[] (a sphere's far hit)
+constexpr uint32_t HIT_INVERT = 1u << 28;  // Primitive.Invert of the hit primitive: its own inside flag is INSIDE ^ INVERT
+constexpr int HIT_KIND_SHIFT = 26;         // 2 bits: DK_* of the hit primitive (k_shade completes flat triangles and plain
+                                           // spheres from sgeom[] alone)
 
 
 constexpr int kTraceStack = 128;
@@ -106,6 +113,27 @@ template <typename R>
 struct DMat {
   V4<R> emis_ior, diff_shin, spec, refr;
 };
+// f32 mode: emission, diffuse, specular, refraction rgb as 12 halfs (w[0..5], low half first), w[6] = ior, w[7] = shininess
+// as float bits. Colours are radiance scale factors and selection weights: half precision (2^-11 relative) is three orders
+// below the 1 % image tolerance; ior and shininess (up to 1e6 and +inf) keep their float range.
+template <>
+struct alignas(32) DMat<float> {
+  uint32_t w[8];
+};
+
+// What a trace launch writes per ray: Hit.Distance and the hit code (slot | kind | invert | second | inside, or HIT_MISS).
+template <typename R>
+struct THit;
+template <>
+struct alignas(8) THit<float> {
+  float t;
+  uint32_t code;
+};
+template <>
+struct alignas(16) THit<double> {
+  double t;
+  uint32_t code, pad;
+};
 
 template <typename R>
 struct SceneView {
@@ -115,8 +143,7 @@ struct SceneView {
   const DMat<R>* mats;
   const int32_t* aux;      // per slot: xform row (low 30 bits) | REF_VNORMALS_AUX, or -1
   const int32_t* prim_id;  // per slot: Primitive.ID
-  const R* prim_nz;        // per slot: z of the triangle's face normal (x, y sit in the record's w lanes); only
-                           // finalize_hit reads it
+  const V4<R>* sgeom;      // per slot: triangle (N.xyz | flags), sphere (centre.xyz | radius), plane (normal.xyz | 0)
   uint32_t root;           // index of the root inner node
   int32_t n_prims;
   const CNode* qnodes;     // f32 mode only: the quantised 8-wide tree over the bounded primitives
@@ -159,10 +186,11 @@ struct Control {            // device-resident launch control block
 
 template <typename R>
 struct PathView {
-  V4<R>* dir;       // xyz = direction
+  V4<R>* dir;       // xyz = direction; w (f32 mode) = |direction|^2 - 1 where the host handed in a ray that is off unit length
   V4<R>* tint;      // rgb
-  V4<R>* hpos[2];   // xyz = hit position (or ray origin for bounce 0), w = Hit.Distance
-  V4<R>* hnrm[2];   // xyz = hit normal, w = hit code bits
+  V4<R>* hpos;      // xyz = last hit position = next ray origin (camera ray origin at bounce 0); w = f64: Hit.Distance, f32: hit code
+  V4<R>* hnrm;      // xyz = last hit normal, w = hit code bits
+  THit<R>* thit;    // the trace kernel's answer for the current bounce
   V4<R>* radiance;  // rgb of finished paths ((-1,-1,-1) = miss)
   V4<R>* skip_pos;  // optional (rtc_trace_closest only): explicit skip-hit position; nullptr = ray origin
   uint32_t* queue[2];
@@ -185,18 +213,17 @@ struct Kernels {
   // explicit (x,y,sample) list -> rtc_ray (f64) ; used by rtc_camera_rays
   static cudaError_t camera_rays(const LaunchCfg& cfg, const CameraView<R>& cam, const ParamsView<R>& par, int64_t n,
                                  const int32_t* xy, const uint32_t* sample, rtc_ray* out);
-  // bounce `bounce`: reads queue[q] (nullptr semantics: identity when bounce == 0), hit buffer `prev`, writes `cur`
-  static cudaError_t trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, int prev, int cur,
-                           bool identity_queue);
+  // bounce `bounce`: reads queue[q] (nullptr semantics: identity when bounce == 0) and the paths' hpos / dir, writes thit
+  static cudaError_t trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, bool identity_queue);
   static cudaError_t shade(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,
-                           const PathView<R>& pv, int q, int cur, int bounce, bool identity_queue);
+                           const PathView<R>& pv, int q, int bounce, bool identity_queue);
   static cudaError_t compact(const LaunchCfg& cfg, const PathView<R>& pv, int q, bool identity_queue);
   static cudaError_t accumulate(const LaunchCfg& cfg, const ParamsView<R>& par, const Band& band, const PathView<R>& pv,
                                 double* rgb_sum, uint32_t* samples, uint32_t* misses);
   // rtc_trace_closest plumbing
   static cudaError_t import_rays(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const rtc_ray* rays,
-                                 const rtc_hit* skip, const int32_t* id_to_slot, const PathView<R>& pv, int prev);
-  static cudaError_t export_hits(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const PathView<R>& pv, int cur,
+                                 const rtc_hit* skip, const int32_t* id_to_slot, const PathView<R>& pv);
+  static cudaError_t export_hits(const LaunchCfg& cfg, const SceneView<R>& sc, int64_t n, const PathView<R>& pv,
                                  rtc_hit* out, bool finalize);
   static cudaError_t export_radiance(const LaunchCfg& cfg, const Band& band, const ParamsView<R>& par,
                                      const PathView<R>& pv, double* out_rgb);
@@ -204,7 +231,7 @@ struct Kernels {
   static cudaError_t overlay_rays(const LaunchCfg& cfg, const CameraView<R>& cam, const ParamsView<R>& par, const Band& band,
                                   const PathView<R>& pv);
   static cudaError_t overlay_prims(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,
-                                   const PathView<R>& pv, int cur, int32_t* out);
+                                   const PathView<R>& pv, int32_t* out);
   static int trace_blocks_per_sm(size_t smem);
 };
 

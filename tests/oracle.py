@@ -31,6 +31,7 @@ def _load():
     lib.orc_render_samples.argtypes = [P, C.c_uint32, C.c_int, P]
     lib.orc_debug_trace.argtypes = [P, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(N.DebugRay), C.POINTER(C.c_int32)]
     lib.orc_debug_raycast.argtypes = [P, C.c_int32, P]
+    lib.orc_set_selfhit_mode.argtypes = [C.c_int]
     lib.orc_dump_path_rays.restype = C.c_int64
     lib.orc_dump_path_rays.argtypes = [P, C.c_int64, P, P, C.c_int, C.c_int64, P, P, P, P]
     lib.orc_tonemap.argtypes = [C.c_int32, C.c_int32, P, P, P, C.c_double, C.POINTER(C.c_double), C.c_double, P]
@@ -134,6 +135,11 @@ class OracleScene:
         n = C.c_int32()
         lib.orc_debug_trace(self._h, x, y, sample, capacity, buf, C.byref(n))
         return [buf[i] for i in range(n.value)]
+
+
+def set_selfhit_mode(mode):
+    """0: the reference's self-hit rule; 1: the f32 mode's documented rule restated in f64 (see rtc_oracle.h)."""
+    lib.orc_set_selfhit_mode(int(mode))
 
 
 def tonemap(rgb, samples, misses, exposure=1.0, back=(0.0, 0.0, 0.0), back_a=0.0):
