@@ -120,6 +120,7 @@ namespace RaytracerCore.Raytracing.Gpu
 		[DllImport(Lib)] public static extern int rtc_comm_unique_id(byte* id128);
 		[DllImport(Lib)] public static extern int rtc_comm_init(IntPtr ctx, int nRanks, int rank, byte* id128);
 		[DllImport(Lib)] public static extern int rtc_reduce_accum(IntPtr ctx, int root);
+		[DllImport(Lib)] public static extern int rtc_bcast_scene(IntPtr ctx, int root);
 		[DllImport(Lib)] public static extern int rtc_comm_destroy(IntPtr ctx);
 
 		public static void Check(IntPtr ctx, int rc)

@@ -278,6 +278,13 @@ int rtc_comm_init(rtc_ctx* ctx, int32_t nranks, int32_t rank, const void* id128)
  * rtc_clear_accum / rtc_write_accum / a size change start a fresh contribution on the calling rank. Collective: all ranks
  * of the communicator must call it with the same root. */
 int rtc_reduce_accum(rtc_ctx* ctx, int32_t root);
+/* Multi-GPU Start(): the device scene of `root` (tree, primitive records, materials -- what rtc_upload_bvh, rtc_build_bvh or
+ * rtc_upload_baked left there) is copied to every other rank of the communicator with ncclBroadcast over NVLink, so the scene
+ * crosses PCIe once per node instead of once per GPU and Scene.Prepare (Scene.cs:39-49) runs on one rank only. The receiving
+ * contexts need no rtc_upload_scene / rtc_upload_bvh; like after rtc_upload_baked of a foreign image they hold no host-side
+ * description (rtc_bake, rtc_get_bvh and the bounding-volume overlay report RTC_ERR_STATE). Camera and parameters are set
+ * per rank as usual. Collective: every rank calls it with the same root, contexts of the same arithmetic mode. */
+int rtc_bcast_scene(rtc_ctx* ctx, int32_t root);
 int rtc_comm_destroy(rtc_ctx* ctx);
 
 #ifdef __cplusplus

@@ -865,6 +865,42 @@ uint64_t orc_render(orc_scene* s, int32_t x0, int32_t y0, int32_t x1, int32_t y1
   return rays.load();
 }
 
+// The same loop over a lattice of the whole frame: pixels (off_x + i * stride_x, off_y + j * stride_y). A bounded sample of a
+// frame that keeps its mix of rays (silhouettes, background, every depth of the scene) -- bench.py's CPU legs.
+uint64_t orc_render_lattice(orc_scene* s, int32_t stride_x, int32_t stride_y, int32_t off_x, int32_t off_y, uint32_t first_sample,
+                            uint32_t n_samples, int threads, double* rgb_sum, uint32_t* samples, uint32_t* misses) {
+  const int w = s->par.width, h = s->par.height;
+  if (stride_x < 1 || stride_y < 1 || off_x < 0 || off_y < 0) return 0;
+  const int rows = off_y < h ? (h - off_y + stride_y - 1) / stride_y : 0;
+  std::atomic<uint64_t> rays{0};
+  parallel_for(rows, threads, 1, [&](int64_t b, int64_t e, int) {
+    PathCtx ctx;
+    ctx.list.reserve(64);
+    for (int64_t j = b; j < e; j++) {
+      const int y = off_y + (int)j * stride_y;
+      for (int x = off_x; x < w; x += stride_x) {
+        const size_t px = (size_t)y * w + x;
+        for (uint32_t k = 0; k < n_samples; k++) {
+          const uint32_t smp = first_sample + k;
+          Ray r = get_camera_ray(*s, x, y, smp);
+          double c[3];
+          get_color(*s, r, (uint32_t)px, smp, ctx, c, nullptr, 0, nullptr);
+          if (c[0] == -1 && c[1] == -1 && c[2] == -1) {
+            misses[px]++;
+          } else {
+            rgb_sum[px * 3 + 0] += c[0];
+            rgb_sum[px * 3 + 1] += c[1];
+            rgb_sum[px * 3 + 2] += c[2];
+            samples[px]++;
+          }
+        }
+      }
+    }
+    rays += ctx.rays;
+  });
+  return rays.load();
+}
+
 void orc_render_samples(orc_scene* s, uint32_t sample, int threads, double* out_rgb) {
   const int w = s->par.width, h = s->par.height;
   parallel_for(h, threads, 1, [&](int64_t b, int64_t e, int) {

@@ -54,6 +54,10 @@ void orc_camera_rays(orc_scene* s, int64_t n, const int32_t* xy, const uint32_t*
  * Scene.RayTrace calls made. */
 uint64_t orc_render(orc_scene* s, int32_t x0, int32_t y0, int32_t x1, int32_t y1, uint32_t first_sample,
                     uint32_t n_samples, int threads, double* rgb_sum, uint32_t* samples, uint32_t* misses);
+/* The same over a lattice of the whole frame, pixels (off_x + i stride_x, off_y + j stride_y): a bounded sample that keeps
+ * the frame's mix of rays (bench.py's CPU legs). */
+uint64_t orc_render_lattice(orc_scene* s, int32_t stride_x, int32_t stride_y, int32_t off_x, int32_t off_y, uint32_t first_sample,
+                            uint32_t n_samples, int threads, double* rgb_sum, uint32_t* samples, uint32_t* misses);
 
 /* One sample of every pixel, raw GetColor output (Placeholder = -1,-1,-1 for misses). out: w*h*3. */
 void orc_render_samples(orc_scene* s, uint32_t sample, int threads, double* out_rgb);

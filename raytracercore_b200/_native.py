@@ -7,7 +7,11 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("RTC_B200_LIB") or os.path.join(_HERE, "librtcore_b200.so")  # env override: kernel-variant A/B runs
+# RTC_B200_HOST_ONLY=1 (bench.py --impl reference): only the scene half of the host mirror (librtcore_host.so: SceneLoader,
+# synthetic scenes, BVH builder) is loaded -- the process maps no CUDA library and the rtc_* / rtcs_raytracer_* calls do not exist
+HOST_ONLY = os.environ.get("RTC_B200_HOST_ONLY") == "1"
+LIB_PATH = os.path.join(_HERE, "librtcore_host.so") if HOST_ONLY else (
+    os.environ.get("RTC_B200_LIB") or os.path.join(_HERE, "librtcore_b200.so"))  # env override: kernel-variant A/B runs
 
 RTC_OK, RTC_ERR_INVALID, RTC_ERR_CUDA, RTC_ERR_STATE, RTC_ERR_NOMEM, RTC_ERR_UNSUPPORTED, RTC_ERR_NCCL = range(7)
 RTC_F32, RTC_F64 = 0, 1
@@ -115,6 +119,7 @@ SIGNATURES = {
     "rtc_comm_unique_id": (C.c_int, [_P]),
     "rtc_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "rtc_reduce_accum": (C.c_int, [_P, C.c_int32]),
+    "rtc_bcast_scene": (C.c_int, [_P, C.c_int32]),
     "rtc_comm_destroy": (C.c_int, [_P]),
     # rtcore_host.h
     "rtcs_scene_load": (_P, [C.c_char_p, C.c_char_p, C.c_int32]),
@@ -155,6 +160,8 @@ def _load():
             "there is no fallback implementation." % LIB_PATH)
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
+        if HOST_ONLY and not (name.startswith("rtcs_scene_") or name == "rtcs_build_bvh"):
+            continue
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args

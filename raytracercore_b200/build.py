@@ -15,6 +15,10 @@ CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "librtcore_b200.so")
+# the scene half of the host mirror alone (SceneLoader, synthetic scenes, BVH builder; no CUDA): what bench.py's
+# `--impl reference` arm loads, so that the CPU process maps no CUDA library
+HOST_LIB = os.path.join(HERE, "librtcore_host.so")
+HOST_ONLY_SOURCES = ("scene.cpp", "scene_loader.cpp", "bvh_builder.cpp", "host_api.cpp")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -64,7 +68,7 @@ def build(force=False, verbose=False):
     headers += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
     all_src = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu")]
     all_src += [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".cpp")]
-    if not force and not _newer(LIB, all_src + headers):
+    if not force and not _newer(LIB, all_src + headers) and os.path.exists(HOST_LIB):
         return LIB  # up to date (also the case on the GPU box, where the prebuilt library travels with the snapshot)
     objs = []
     units = [
@@ -91,6 +95,9 @@ def build(force=False, verbose=False):
         objs.append(o)
     if force or _newer(LIB, objs):
         _run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl", "-lpthread"])
+    host_objs = [os.path.join(OBJ, f + ".o") for f in HOST_ONLY_SOURCES]
+    if LIB.endswith("librtcore_b200.so") and (force or _newer(HOST_LIB, host_objs)):
+        _run([cxx, "-shared", "-o", HOST_LIB] + host_objs + ["-lpthread"])
     return LIB
 
 

@@ -34,6 +34,7 @@ struct NcclApi {
   int (*CommDestroy)(void*) = nullptr;
   int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -53,10 +54,11 @@ struct NcclApi {
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     Reduce = (decltype(Reduce))dlsym(lib, "ncclReduce");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    Broadcast = (decltype(Broadcast))dlsym(lib, "ncclBroadcast");
     GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
     GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !Reduce || !AllReduce || !GroupStart || !GroupEnd) {
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !Reduce || !AllReduce || !Broadcast || !GroupStart || !GroupEnd) {
       err = "libnccl is missing required symbols";
       return false;
     }
@@ -64,7 +66,7 @@ struct NcclApi {
   }
 };
 NcclApi g_nccl;
-constexpr int kNcclFloat64 = 8, kNcclUint32 = 3, kNcclSum = 0;
+constexpr int kNcclFloat64 = 8, kNcclUint32 = 3, kNcclUint8 = 1, kNcclSum = 0;
 
 struct TimedLaunch {
   cudaEvent_t a, b;
@@ -131,6 +133,7 @@ struct rtc_ctx {
   uint32_t root_node = 0;
   int bvh_depth = 0;
   size_t seg_cap[rtc_baked::S_COUNT] = {0};  // device capacity per scene segment (buffers are reused across uploads)
+  size_t seg_bytes[rtc_baked::S_COUNT] = {0};  // bytes of each segment in use by the current device scene
   rtc_baked* baked = nullptr;               // image of the current device scene
 
   // path pool
@@ -501,6 +504,7 @@ int upload_baked_image(rtc_ctx* ctx, const rtc_baked* bk) {
   ctx->n_unbounded = bk->n_unbounded;
   ctx->root_node = bk->root_node;
   ctx->bvh_depth = bk->bvh_depth;
+  for (int i = 0; i < rtc_baked::S_COUNT; i++) ctx->seg_bytes[i] = bk->bytes[i];
   if (!bk->pinned) CU(cudaStreamSynchronize(ctx->stream));
   return RTC_OK;
 }
@@ -2164,6 +2168,120 @@ int rtc_reduce_accum(rtc_ctx* ctx, int32_t root) {
     ctx->replicated = true;
   }
   return after_accum_write(ctx);
+}
+
+// What a receiving rank needs to know about the root's device scene before the segments arrive.
+struct SceneHeader {
+  int32_t precision, n_prims, n_unbounded, n_xforms, bvh_depth;
+  uint32_t root_node;
+  uint64_t bytes[rtc_baked::S_COUNT];
+};
+
+int rtc_bcast_scene(rtc_ctx* ctx, int32_t root) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!ctx->nccl_comm) return fail(ctx, RTC_ERR_STATE, "rtc_comm_init has not been called");
+  if (root < 0 || root >= ctx->nranks) return fail(ctx, RTC_ERR_INVALID, "root out of range");
+  cudaSetDevice(ctx->device);
+  const bool is_root = ctx->rank == root;
+  if (is_root) {
+    int rc = ready(ctx, false);
+    if (rc) return rc;
+    rc = wait_shading_upload(ctx);  // the shading half of a staged upload may still be in flight on the copy stream
+    if (rc) return rc;
+  }
+  auto nccl_fail = [&](int r, const char* what) {
+    return fail(ctx, RTC_ERR_NCCL, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+  };
+  // 1. the header: precision, counts and the byte length of every segment
+  SceneHeader* h_hdr = nullptr;
+  void* d_hdr = nullptr;
+  CU(cudaMallocHost((void**)&h_hdr, sizeof(SceneHeader)));
+  cudaError_t ce = cudaMalloc(&d_hdr, sizeof(SceneHeader));
+  if (ce != cudaSuccess) {
+    cudaFreeHost(h_hdr);
+    return fail(ctx, RTC_ERR_CUDA, cudaGetErrorString(ce));
+  }
+  std::memset(h_hdr, 0, sizeof(SceneHeader));
+  if (is_root) {
+    h_hdr->precision = ctx->precision;
+    h_hdr->n_prims = ctx->n_prims;
+    h_hdr->n_unbounded = ctx->n_unbounded;
+    h_hdr->n_xforms = ctx->n_xforms;
+    h_hdr->bvh_depth = ctx->bvh_depth;
+    h_hdr->root_node = ctx->root_node;
+    for (int i = 0; i < rtc_baked::S_COUNT; i++) h_hdr->bytes[i] = ctx->seg_bytes[i];
+    cudaMemcpyAsync(d_hdr, h_hdr, sizeof(SceneHeader), cudaMemcpyHostToDevice, ctx->stream);
+  }
+  int r = g_nccl.Broadcast(d_hdr, d_hdr, sizeof(SceneHeader), kNcclUint8, root, ctx->nccl_comm, ctx->stream);
+  if (r == 0) {
+    cudaMemcpyAsync(h_hdr, d_hdr, sizeof(SceneHeader), cudaMemcpyDeviceToHost, ctx->stream);
+    ce = cudaStreamSynchronize(ctx->stream);
+  }
+  const SceneHeader hdr = *h_hdr;
+  cudaFreeHost(h_hdr);
+  cudaFree(d_hdr);
+  if (r != 0) return nccl_fail(r, "ncclBroadcast (scene header)");
+  if (ce != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, cudaGetErrorString(ce));
+  // every rank returns the same verdict on a mode mismatch (no rank is left waiting in the second collective)
+  if (hdr.precision != ctx->precision) return fail(ctx, RTC_ERR_INVALID, "the root's scene was made for the other arithmetic mode");
+  // 2. the segments, into (reused) device buffers
+  void** dst[rtc_baked::S_COUNT] = {&ctx->d_nodes, &ctx->d_qnodes, (void**)&ctx->d_unbounded, &ctx->d_prims, &ctx->d_mats,
+                                    &ctx->d_xforms, (void**)&ctx->d_aux, (void**)&ctx->d_prim_id, (void**)&ctx->d_id_to_slot,
+                                    &ctx->d_sgeom};
+  if (!is_root) {
+    if (ctx->shading_pending) {
+      int rc = wait_shading_upload(ctx);
+      if (rc) return rc;
+    }
+    for (int i = 0; i < rtc_baked::S_COUNT; i++) {
+      const size_t need = std::max<size_t>((size_t)hdr.bytes[i], 16);
+      if (ctx->seg_cap[i] < need || !*dst[i]) {
+        if (*dst[i]) {
+          CU(cudaStreamSynchronize(ctx->stream));
+          cudaFree(*dst[i]);
+          *dst[i] = nullptr;
+        }
+        CU(cudaMalloc(dst[i], need));
+        ctx->seg_cap[i] = need;
+      }
+    }
+  }
+  r = g_nccl.GroupStart();
+  if (r == 0) {
+    for (int i = 0; i < rtc_baked::S_COUNT && r == 0; i++)
+      if (hdr.bytes[i]) r = g_nccl.Broadcast(*dst[i], *dst[i], (size_t)hdr.bytes[i], kNcclUint8, root, ctx->nccl_comm, ctx->stream);
+    int r2 = g_nccl.GroupEnd();
+    if (r == 0) r = r2;
+  }
+  if (r != 0) return nccl_fail(r, "ncclBroadcast (scene segments)");
+  if (!is_root) {
+    if (hdr.bytes[rtc_baked::S_QNODES] == 0 && hdr.precision == RTC_F32 && ctx->d_qnodes) {  // the kernel keys on a null pointer
+      CU(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_qnodes);
+      ctx->d_qnodes = nullptr;
+      ctx->seg_cap[rtc_baked::S_QNODES] = 0;
+    }
+    ctx->n_prims = hdr.n_prims;
+    ctx->n_xforms = hdr.n_xforms;
+    ctx->n_unbounded = hdr.n_unbounded;
+    ctx->bvh_depth = hdr.bvh_depth;
+    ctx->root_node = hdr.root_node;
+    for (int i = 0; i < rtc_baked::S_COUNT; i++) ctx->seg_bytes[i] = (size_t)hdr.bytes[i];
+    // no host-side description behind this scene (as after rtc_upload_baked of a foreign image)
+    ctx->kind.clear();
+    ctx->flags.clear();
+    ctx->geom.clear();
+    ctx->material.clear();
+    ctx->xform.clear();
+    ctx->xforms.clear();
+    ctx->nodes.clear();
+    ctx->root = -1;
+    delete ctx->baked;
+    ctx->baked = nullptr;
+    ctx->scene_set = true;
+    ctx->bvh_set = true;
+  }
+  return RTC_OK;
 }
 
 int rtc_comm_destroy(rtc_ctx* ctx) {

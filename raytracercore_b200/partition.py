@@ -40,3 +40,35 @@ def run_frame(ctx, frame, rank, world, spp, root=0, strong=False, clear=False):
     if world > 1:
         ctx.reduce_accum(root)
     return first, count
+
+
+def check_reduced_frame(job, spp):
+    """bench.py's in-run check at N > 1 (collective: every rank calls it). One weak-split frame is rendered by all ranks and
+    reduced to rank 0; rank 0 then renders the same world * spp samples of every pixel alone. The reduced planes must equal
+    the single-GPU ones: `samples` and `misses` bit for bit (and samples + misses == world * spp everywhere), the f64 colour
+    sums to 1e-12 relative (the summation order differs between the two). Returns a small report on rank 0, None elsewhere."""
+    import numpy as np
+    env, ctx = job.env, job.ctx
+    rank, world = env["rank"], env["world"]
+    ctx.clear_accum()
+    run_frame(ctx, 0, rank, world, spp)
+    got = ctx.read_accum() if rank == 0 else None
+    ctx.sync()
+    env["barrier"]()
+    report = None
+    if rank == 0:
+        ctx.clear_accum()
+        ctx.render(*frame_samples(0, world, spp))
+        w_rgb, w_s, w_m = ctx.read_accum()
+        rgb, s, m = got
+        exact = bool(np.array_equal(s, w_s) and np.array_equal(m, w_m))
+        total_ok = bool(np.all(s.astype(np.int64) + m == world * spp))
+        scale = np.maximum(np.abs(w_rgb), 1e-300)
+        rel = float(np.max(np.abs(rgb - w_rgb) / scale)) if rgb.size else 0.0
+        close = bool(np.allclose(rgb, w_rgb, rtol=1e-12, atol=1e-12))
+        report = {"result": "green" if (exact and total_ok and close) else "red", "counters_bit_exact": exact,
+                  "samples_plus_misses_equal_n_spp": total_ok, "max_rel_diff_rgb_sum": rel, "samples_per_pixel": world * spp,
+                  "what": "reduced planes of one frame over N ranks vs rank 0's own render of the same N x spp samples"}
+    ctx.clear_accum()
+    env["barrier"]()
+    return report

@@ -246,6 +246,10 @@ class Context:
     def reduce_accum(self, root=0):
         self._ck(N.lib.rtc_reduce_accum(self._h, root))
 
+    def bcast_scene(self, root=0):
+        """Collective: every rank receives root's device scene over NVLink (no rtc_upload_scene / rtc_upload_bvh on the others)."""
+        self._ck(N.lib.rtc_bcast_scene(self._h, root))
+
 
 class FullRaytracer:
     """Mirror of FullRaytracer (Raytracing/FullRaytracer.cs): Start() blocks; Stop/Pause/Resume from other threads."""

@@ -28,6 +28,8 @@ def _load():
     lib.orc_camera_rays.argtypes = [P, C.c_int64, P, P, P]
     lib.orc_render.restype = C.c_uint64
     lib.orc_render.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_int, P, P, P]
+    lib.orc_render_lattice.restype = C.c_uint64
+    lib.orc_render_lattice.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_int, P, P, P]
     lib.orc_render_samples.argtypes = [P, C.c_uint32, C.c_int, P]
     lib.orc_debug_trace.argtypes = [P, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(N.DebugRay), C.POINTER(C.c_int32)]
     lib.orc_debug_raycast.argtypes = [P, C.c_int32, P]
@@ -107,6 +109,16 @@ class OracleScene:
                      np.zeros((self.height, self.width), np.uint32))
         rgb, s, m = accum
         rays = lib.orc_render(self._h, x0, y0, x1, y1, first_sample, n_samples, threads, _ptr(rgb), _ptr(s), _ptr(m))
+        return rgb, s, m, int(rays)
+
+    def render_lattice(self, stride, offset, first_sample, n_samples, threads=NTHREADS, accum=None):
+        """orc_render over the lattice of pixels (offset[0] + i stride[0], offset[1] + j stride[1]) of the whole frame."""
+        if accum is None:
+            accum = (np.zeros((self.height, self.width, 3)), np.zeros((self.height, self.width), np.uint32),
+                     np.zeros((self.height, self.width), np.uint32))
+        rgb, s, m = accum
+        rays = lib.orc_render_lattice(self._h, stride[0], stride[1], offset[0], offset[1], first_sample, n_samples, threads,
+                                      _ptr(rgb), _ptr(s), _ptr(m))
         return rgb, s, m, int(rays)
 
     def render_samples(self, sample, threads=NTHREADS):

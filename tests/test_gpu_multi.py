@@ -80,3 +80,44 @@ def test_reduced_frames_equal_the_single_gpu_render(root):
                     assert not got[r][f][1].any() and not got[r][f][2].any() and not got[r][f][0].any()
     for c in ctxs:
         c.close()
+
+
+def test_scene_broadcast_over_nvlink_gives_every_rank_the_roots_scene():
+    """rtc_bcast_scene: only rank 0 prepares and uploads the scene; the other ranks receive the device image with ncclBroadcast
+    and, given the same camera and parameters, must render bit-identical planes -- for a scene that replaces an earlier one
+    of a different size on the receivers as well. A receiving context has no host-side description (rtc_bake fails)."""
+    n_dev = N.lib.rtc_device_count()
+    if n_dev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(n_dev, 4)
+    scenes = [Scene.from_file(os.path.join(SCENES, "cornell_bounce.scene")), Scene.synthetic("soup", 30000, 5, 0.02),
+              Scene.from_file(os.path.join(SCENES, "die.scene"))]
+    for sc in scenes:
+        sc.override(width=80, height=48, recursion=4)
+    uid = Context.comm_unique_id()
+    ctxs = [Context(r, RTC_F32) for r in range(world)]
+    got = [[None] * len(scenes) for _ in range(world)]
+
+    def rank_main(r):
+        c = ctxs[r]
+        c.comm_init(world, r, uid)
+        for k, sc in enumerate(scenes):
+            if r == 0:
+                c.load(sc, seed=4)
+            c.bcast_scene(0)
+            if r != 0:
+                c.set_params(sc.params(4))
+                c.set_camera(sc.camera())
+                with pytest.raises(N.RtcError):
+                    c.bake()
+            c.clear_accum()
+            c.render(0, 2)
+            got[r][k] = c.read_accum()
+
+    _run_ranks(world, rank_main)
+    for k in range(len(scenes)):
+        for r in range(1, world):
+            assert all(np.array_equal(a, b) for a, b in zip(got[r][k], got[0][k])), (k, r)
+        assert got[0][k][1].any()
+    for c in ctxs:
+        c.close()

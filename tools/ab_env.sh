@@ -3,5 +3,5 @@
 log=$1; var=$2; vals=$3; shift 3
 for v in $vals; do
   echo "== $var=$v" >> $log
-  env $var=$v python tools/prof_step.py "$@" 2>&1 | grep -v "^  [rsca]" >> $log
+  env $var=$v python tools/prof_step.py "$@" 2>&1 | grep -v "^  [rca]" >> $log
 done
