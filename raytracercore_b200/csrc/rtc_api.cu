@@ -142,7 +142,14 @@ struct rtc_ctx {
   void *d_dir = nullptr, *d_tint = nullptr, *d_hpos = nullptr, *d_hnrm = nullptr, *d_thit = nullptr, *d_radiance = nullptr,
        *d_skip_pos = nullptr;
   uint32_t* d_queue[2] = {nullptr, nullptr};
-  Control* d_ctl = nullptr;
+  Control* d_ctl = nullptr;  // [2]: one control block per wavefront in flight
+  // Two wavefronts in flight (rtc_render): the bands of a frame alternate between the context's stream and wave_stream, each
+  // with its own half of the path pool and its own control block, so that the drain phase of one band's persistent trace
+  // launch (few rays left, most SMs idle) is filled by the other band's kernels. Bands are disjoint pixel rows: the
+  // accumulation stays race-free and ordered per pixel. RTC_OPT_WAVES = 1 serialises (as does RTC_OPT_KERNEL_TIMING).
+  int waves = 2;
+  cudaStream_t wave_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_accum2 = nullptr;
   int32_t* d_dbg_type = nullptr;
   void* d_dbg_fresnel = nullptr;
   // rtc_trace_closest staging
@@ -184,7 +191,7 @@ struct rtc_ctx {
   std::mutex ev_mutex;    // guards ev_accum / ev_ui_done bookkeeping between the render thread and the read-out thread
   cudaStream_t ui_stream = nullptr;
   cudaEvent_t ev_accum = nullptr, ev_ui_done = nullptr;
-  bool accum_recorded = false, ui_pending = false;
+  bool accum_recorded = false, accum2_recorded = false, ui_pending = false;
   uint32_t *d_argb = nullptr, *h_argb = nullptr;  // persistent ARGB8 image: device + pinned host staging
   size_t argb_cap = 0;
   double* h_pixel = nullptr;  // pinned: rgb[3] + samples + misses of one pixel
@@ -239,20 +246,27 @@ int ensure_scratch(rtc_ctx* ctx, size_t bytes) {
 }
 
 // Render-thread side of the read-out protocol: called right before a launch that writes the accumulation planes ...
-int before_accum_write(rtc_ctx* ctx) {
+int before_accum_write(rtc_ctx* ctx, int wave = 0) {
   std::lock_guard<std::mutex> g(ctx->ev_mutex);
   if (ctx->ui_pending) {  // a tonemap / pixel read is (or was) in flight on ui_stream: the planes must not change under it
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_ui_done, 0));
+    if (ctx->wave_stream) CU(cudaStreamWaitEvent(ctx->wave_stream, ctx->ev_ui_done, 0));
     ctx->ui_pending = false;
   }
+  (void)wave;
   return RTC_OK;
 }
 // ... and right after it
-int after_accum_write(rtc_ctx* ctx) {
+int after_accum_write(rtc_ctx* ctx, int wave = 0) {
   if (!ctx->ev_accum) return RTC_OK;  // no read-out has ever been asked for
   std::lock_guard<std::mutex> g(ctx->ev_mutex);
-  CU(cudaEventRecord(ctx->ev_accum, ctx->stream));
-  ctx->accum_recorded = true;
+  if (wave == 0) {
+    CU(cudaEventRecord(ctx->ev_accum, ctx->stream));
+    ctx->accum_recorded = true;
+  } else {
+    CU(cudaEventRecord(ctx->ev_accum2, ctx->wave_stream));
+    ctx->accum2_recorded = true;
+  }
   return RTC_OK;
 }
 // Read-out side: order ui_stream behind every write to the planes issued so far
@@ -265,6 +279,7 @@ int ui_begin(rtc_ctx* ctx) {
     ctx->accum_recorded = true;
   }
   CU(cudaStreamWaitEvent(ctx->ui_stream, ctx->ev_accum, 0));
+  if (ctx->accum2_recorded) CU(cudaStreamWaitEvent(ctx->ui_stream, ctx->ev_accum2, 0));  // the second wavefront's last accumulate
   return RTC_OK;
 }
 int ui_end(rtc_ctx* ctx) {
@@ -342,25 +357,35 @@ int ensure_pool(rtc_ctx* ctx, int64_t want) {
   for (int i = 0; i < 2; i++) CU(cudaMalloc((void**)&ctx->d_queue[i], sizeof(uint32_t) * want));
   CU(cudaMalloc(&ctx->d_radiance, v4 * want));
   if (!ctx->d_ctl) {
-    CU(cudaMalloc((void**)&ctx->d_ctl, sizeof(Control)));
-    CU(cudaMemset(ctx->d_ctl, 0, sizeof(Control)));
+    CU(cudaMalloc((void**)&ctx->d_ctl, 2 * sizeof(Control)));
+    CU(cudaMemset(ctx->d_ctl, 0, 2 * sizeof(Control)));
   }
   ctx->pool_cap = want;
   return RTC_OK;
 }
 
+int ensure_wave_stream(rtc_ctx* ctx) {
+  if (ctx->wave_stream) return RTC_OK;
+  CU(cudaStreamCreateWithFlags(&ctx->wave_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->ev_accum2, cudaEventDisableTiming));
+  return RTC_OK;
+}
+
+// wave 1 works in the upper part of every pool array, from element `offset` on, with the second control block
 template <typename R>
-PathView<R> path_view(rtc_ctx* c) {
+PathView<R> path_view(rtc_ctx* c, int wave = 0, int64_t offset = 0) {
   PathView<R> pv;
-  pv.dir = (V4<R>*)c->d_dir;
-  pv.tint = (V4<R>*)c->d_tint;
-  pv.hpos = (V4<R>*)c->d_hpos;
-  pv.hnrm = (V4<R>*)c->d_hnrm;
-  pv.thit = (THit<R>*)c->d_thit;
-  for (int i = 0; i < 2; i++) pv.queue[i] = c->d_queue[i];
-  pv.radiance = (V4<R>*)c->d_radiance;
+  pv.dir = (V4<R>*)c->d_dir + offset;
+  pv.tint = (V4<R>*)c->d_tint + offset;
+  pv.hpos = (V4<R>*)c->d_hpos + offset;
+  pv.hnrm = (V4<R>*)c->d_hnrm + offset;
+  pv.thit = (THit<R>*)c->d_thit + offset;
+  for (int i = 0; i < 2; i++) pv.queue[i] = c->d_queue[i] + offset;
+  pv.radiance = (V4<R>*)c->d_radiance + offset;
   pv.skip_pos = nullptr;
-  pv.ctl = c->d_ctl;
+  pv.ctl = c->d_ctl + wave;
   pv.dbg_type = nullptr;
   pv.dbg_fresnel = nullptr;
   return pv;
@@ -1167,18 +1192,19 @@ void drain_timing(rtc_ctx* c) {
 struct Timed {
   rtc_ctx* c;
   int kind;
+  cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
-  Timed(rtc_ctx* ctx, int k) : c(ctx), kind(k) {
+  Timed(rtc_ctx* ctx, int k, cudaStream_t stream = nullptr) : c(ctx), kind(k), st(stream ? stream : ctx->stream) {
     c->stats.launches[k]++;
     if (c->timing) {
       a = get_event(c);
       b = get_event(c);
-      cudaEventRecord(a, c->stream);
+      cudaEventRecord(a, st);
     }
   }
   ~Timed() {
     if (c->timing) {
-      cudaEventRecord(b, c->stream);
+      cudaEventRecord(b, st);
       c->pending.push_back({a, b, kind});
       if (c->pending.size() > 8192) drain_timing(c);
     }
@@ -1187,10 +1213,11 @@ struct Timed {
 
 // One wavefront over `band`: raygen, (trace, shade + compaction, bookkeeping) x (recursion+1), then accumulate or export.
 template <typename R>
-int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb, bool debug) {
-  LaunchCfg cfg{ctx->stream, ctx->sm_count, ctx->counters};
+int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb, bool debug, int wave = 0, int64_t pool_offset = 0) {
+  cudaStream_t stream = wave ? ctx->wave_stream : ctx->stream;
+  LaunchCfg cfg{stream, ctx->sm_count, ctx->counters};
   SceneView<R> sv = scene_view<R>(ctx);
-  PathView<R> pv = path_view<R>(ctx);
+  PathView<R> pv = path_view<R>(ctx, wave, pool_offset);
   if (debug) {
     pv.dbg_type = ctx->d_dbg_type;
     pv.dbg_fresnel = (R*)ctx->d_dbg_fresnel;
@@ -1198,7 +1225,7 @@ int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb,
   CameraView<R> cv = camera_view<R>(ctx->cam);
   ParamsView<R> par = params_view<R>(ctx->par);
   {
-    Timed t(ctx, RTC_K_RAYGEN);
+    Timed t(ctx, RTC_K_RAYGEN, stream);
     CU(Kernels<R>::raygen(cfg, cv, par, band, pv));
   }
   ctx->stats.paths += band.n_paths;
@@ -1207,30 +1234,30 @@ int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb,
     const int q = i & 1;
     const bool ident = (i == 0);
     {
-      Timed t(ctx, RTC_K_TRACE);
+      Timed t(ctx, RTC_K_TRACE, stream);
       CU(Kernels<R>::trace(cfg, sv, pv, q, ident));
     }
-    if (i == 0) {
+    if (i == 0 && wave == 0) {
       int rcw = wait_shading_upload(ctx);  // materials may still be arriving behind the first trace launch
       if (rcw) return rcw;
     }
     {
-      Timed t(ctx, RTC_K_SHADE);
+      Timed t(ctx, RTC_K_SHADE, stream);
       CU(Kernels<R>::shade(cfg, sv, par, band, pv, q, i, ident));
     }
     {
-      Timed t(ctx, RTC_K_COMPACT);
+      Timed t(ctx, RTC_K_COMPACT, stream);
       CU(Kernels<R>::compact(cfg, pv, q, ident));
     }
   }
   if (accumulate) {
-    int rcu = before_accum_write(ctx);
+    int rcu = before_accum_write(ctx, wave);
     if (rcu) return rcu;
     {
-      Timed t(ctx, RTC_K_ACCUMULATE);
+      Timed t(ctx, RTC_K_ACCUMULATE, stream);
       CU(Kernels<R>::accumulate(cfg, par, band, pv, ctx->d_rgb, ctx->d_samples, ctx->d_misses));
     }
-    rcu = after_accum_write(ctx);
+    rcu = after_accum_write(ctx, wave);
     if (rcu) return rcu;
   } else if (d_out_rgb) {
     CU(Kernels<R>::export_radiance(cfg, band, par, pv, d_out_rgb));
@@ -1248,16 +1275,37 @@ struct ReadBack {
 template <typename R>
 int render_rect(rtc_ctx* ctx, int x0, int y0, int x1, int y1, uint32_t first_sample, uint32_t n_samples, bool accumulate,
                 double* d_out_rgb, const ReadBack* rb = nullptr) {
-  const int64_t rw = x1 - x0;
+  const int64_t rw = x1 - x0, rh = y1 - y0;
   const int64_t cap = std::max<int64_t>(ctx->max_paths, rw);
-  int rc = ensure_pool(ctx, std::min<int64_t>(cap, rw * (int64_t)(y1 - y0) * (int64_t)n_samples));
+  const int64_t total = rw * rh * (int64_t)n_samples;
+  // two wavefronts in flight when the frame gives each of them whole 4-row groups and at least 4 Mi paths (measured on the
+  // B200: +2 % on the triangle soups, +1..10 % on the shading-heavy scenes at 16..32 Mi paths per frame, -2..3 % at 2 Mi
+  // paths per wavefront, where halving the launches costs more than their overlap returns); per-kernel event timing keeps
+  // the launches of one stream back to back, so it uses one wavefront
+  const bool dual = ctx->waves > 1 && accumulate && !ctx->timing && rh >= 8 && std::min(total, cap) >= (int64_t)1 << 23 && cap / 2 >= rw * 4;
+  int rc = ensure_pool(ctx, std::min<int64_t>(cap, total));
   if (rc) return rc;
-  int64_t rows_per_band = std::max<int64_t>(1, std::min<int64_t>(y1 - y0, cap / rw));
-  if (rows_per_band >= 4) rows_per_band &= ~(int64_t)3;  // whole 8 x 4 pixel tiles per band (band_pix_xy)
-  for (int ya = y0; ya < y1; ya += (int)rows_per_band) {
+  int64_t cap_w = cap, half = 0;
+  if (dual) {
+    rc = ensure_wave_stream(ctx);
+    if (rc) return rc;
+    half = ctx->pool_cap / 2;
+    cap_w = half;
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));  // the second stream starts behind everything issued so far
+    CU(cudaStreamWaitEvent(ctx->wave_stream, ctx->ev_fork, 0));
+    if (ctx->shading_pending) CU(cudaStreamWaitEvent(ctx->wave_stream, ctx->ev_shading, 0));
+  }
+  int64_t rows_per_band = std::max<int64_t>(1, std::min<int64_t>(rh, cap_w / rw));
+  if (dual && rows_per_band * 2 > rh) rows_per_band = (rh + 1) / 2;  // at least two bands
+  if (rows_per_band >= 4) rows_per_band = dual ? ((rows_per_band + 3) & ~(int64_t)3) : (rows_per_band & ~(int64_t)3);  // whole 8 x 4 pixel tiles per band (band_pix_xy)
+  if (rows_per_band * rw > cap_w) rows_per_band = std::max<int64_t>(4, (cap_w / rw) & ~(int64_t)3);
+  int band_index = 0;
+  for (int ya = y0; ya < y1; ya += (int)rows_per_band, band_index++) {
     int yb = (int)std::min<int64_t>(y1, ya + rows_per_band);
     int64_t npix = rw * (yb - ya);
-    uint32_t s_chunk = (uint32_t)std::max<int64_t>(1, cap / npix);
+    uint32_t s_chunk = (uint32_t)std::max<int64_t>(1, cap_w / npix);
+    const int wave = dual ? (band_index & 1) : 0;
+    cudaStream_t stream = wave ? ctx->wave_stream : ctx->stream;
     for (uint32_t s = 0; s < n_samples; s += s_chunk) {
       Band b;
       b.x0 = x0; b.x1 = x1; b.y0 = ya; b.y1 = yb;
@@ -1265,19 +1313,28 @@ int render_rect(rtc_ctx* ctx, int x0, int y0, int x1, int y1, uint32_t first_sam
       b.n_samples = std::min(s_chunk, n_samples - s);
       b.n_pix = (uint32_t)npix;
       b.n_paths = (uint32_t)(npix * b.n_samples);
-      rc = run_band<R>(ctx, b, accumulate, d_out_rgb, false);
-      if (rc) return rc;
+      rc = run_band<R>(ctx, b, accumulate, d_out_rgb, false, wave, wave ? half : 0);
+      if (rc) break;
     }
+    if (rc) break;
     if (rb) {  // full-width bands: rows [ya, yb) are contiguous in the row-major planes
       const size_t off = (size_t)ya * ctx->acc_w, cnt = (size_t)(yb - ya) * ctx->acc_w;
-      CU(cudaEventRecord(ctx->ev_band, ctx->stream));
+      CU(cudaEventRecord(ctx->ev_band, stream));
       CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band, 0));
       if (rb->rgb) CU(cudaMemcpyAsync(rb->rgb + off * 3, ctx->d_rgb + off * 3, cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
       if (rb->samples) CU(cudaMemcpyAsync(rb->samples + off, ctx->d_samples + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
       if (rb->misses) CU(cudaMemcpyAsync(rb->misses + off, ctx->d_misses + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
   }
-  return RTC_OK;
+  if (dual) {  // the context's stream continues behind both wavefronts (also on an error path: nothing is left dangling)
+    cudaError_t e1 = cudaEventRecord(ctx->ev_join, ctx->wave_stream);
+    cudaError_t e2 = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+    if (!rc) {
+      CU(e1);
+      CU(e2);
+    }
+  }
+  return rc;
 }
 
 int ensure_accum(rtc_ctx* ctx) {
@@ -1344,8 +1401,15 @@ int fetch_device_counters(rtc_ctx* ctx, Control* host) {
     std::memset(host, 0, sizeof(*host));
     return RTC_OK;
   }
-  CU(cudaMemcpyAsync(host, ctx->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
+  Control two[2];
+  CU(cudaMemcpyAsync(two, ctx->d_ctl, 2 * sizeof(Control), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  *host = two[0];
+  host->rays += two[1].rays;
+  host->nodes_visited += two[1].nodes_visited;
+  host->prims_tested += two[1].prims_tested;
+  host->node_steps += two[1].node_steps;
+  host->leaf_steps += two[1].leaf_steps;
   return RTC_OK;
 }
 
@@ -1423,6 +1487,13 @@ void rtc_destroy(rtc_ctx* ctx) {
     cudaEventDestroy(ctx->ev_shading);
     cudaEventDestroy(ctx->ev_band);
   }
+  if (ctx->wave_stream) {
+    cudaStreamSynchronize(ctx->wave_stream);
+    cudaStreamDestroy(ctx->wave_stream);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    cudaEventDestroy(ctx->ev_accum2);
+  }
   if (ctx->ui_stream) {
     cudaStreamSynchronize(ctx->ui_stream);
     cudaStreamDestroy(ctx->ui_stream);
@@ -1460,6 +1531,10 @@ int rtc_set_option(rtc_ctx* ctx, int option, int64_t value) {
   switch (option) {
     case RTC_OPT_KERNEL_TIMING: ctx->timing = value != 0; return RTC_OK;
     case RTC_OPT_COUNTERS: ctx->counters = value != 0; return RTC_OK;
+    case RTC_OPT_WAVES:
+      if (value < 1 || value > 2) return fail(ctx, RTC_ERR_INVALID, "wavefronts in flight must be 1 or 2");
+      ctx->waves = (int)value;
+      return RTC_OK;
     case RTC_OPT_MAX_PATHS:
       if (value < 1024 || value > (int64_t)1 << 28) return fail(ctx, RTC_ERR_INVALID, "max paths must be in [1024, 2^28]");
       if (value != ctx->max_paths) {
@@ -2085,7 +2160,7 @@ int rtc_reset_stats(rtc_ctx* ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   drain_timing(ctx);
   std::memset(&ctx->stats, 0, sizeof(ctx->stats));
-  if (ctx->d_ctl) CU(cudaMemset(ctx->d_ctl, 0, sizeof(Control)));
+  if (ctx->d_ctl) CU(cudaMemset(ctx->d_ctl, 0, 2 * sizeof(Control)));
   return RTC_OK;
 }
 

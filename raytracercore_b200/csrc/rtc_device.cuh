@@ -349,9 +349,9 @@ __device__ __forceinline__ int tri_hits(const SceneView<R>& sc, uint32_t ref, co
     if (ax >= 0 && (ax & REF_VNORMALS_AUX)) {  // :211-219 (weights and the zero face normal are the reference's)
       const DXform<R>* xf = sc.xforms + (ax & 0x3FFFFFFF);
       V3<R> n0 = xyz(ldg4(&xf->r[0])), n1 = xyz(ldg4(&xf->r[1])), n2 = xyz(ldg4(&xf->r[2]));
-      V3<R> nn = normalize3(((n0 * u) + (n1 * v)) + (n2 * (u + v)));
+      V3<R> nn = xnormalize3(((n0 * u) + (n1 * v)) + (n2 * (u + v)));  // (f64: the exact sqrt and divisions)
       if (inside)
-        nn = nn - (N * (2 * (dot3(nn, N)) / dot3(N, N)));
+        nn = nn - (N * xdiv(2 * (dot3(nn, N)), dot3(N, N)));
       out[0].normal = nn;
     } else {
       out[0].normal = inside ? (N * R(-1)) : N;  // :221-223

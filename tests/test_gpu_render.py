@@ -471,3 +471,27 @@ def test_ui_read_out_runs_beside_the_render_loop():
     rgb, s, m = ctx.read_pixel(256, 400)
     assert np.array_equal(np.array(rgb), got[0][400, 256]) and s == got[1][400, 256] and m == got[2][400, 256]
     ctx.close()
+
+
+def test_two_wavefronts_in_flight_render_the_same_planes():
+    """RTC_OPT_WAVES: a frame large enough to be split over two streams (alternate bands, half the path pool each) must give
+    the planes of the one-stream render bit for bit -- bands are disjoint pixel rows and every pixel's samples are still added
+    in ascending order -- for a band count that is odd, a height that is no multiple of the band, and through rtc_render_read."""
+    from raytracercore_b200 import RTC_OPT_MAX_PATHS, RTC_OPT_WAVES
+    sc = cornell(1024, 1004, 4)
+    out = {}
+    for waves in (1, 2):
+        ctx = Context(0, RTC_F32)
+        ctx.set_option(RTC_OPT_WAVES, waves)
+        ctx.set_option(RTC_OPT_MAX_PATHS, 8 << 20)  # 4 Mi paths per wavefront: two uneven bands, two sample chunks each
+        ctx.load(sc, seed=3)
+        ctx.render(0, 9)
+        a = ctx.read_accum()
+        b = ctx.render_read(9, 9)
+        st = ctx.stats()
+        out[waves] = (a, b, st.paths, st.rays)
+        ctx.close()
+    for k in range(2):
+        assert all(np.array_equal(x, y) for x, y in zip(out[1][k], out[2][k]))
+    assert out[1][2:] == out[2][2:]
+    assert np.all(out[2][1][1] + out[2][1][2] == 18)

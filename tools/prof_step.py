@@ -8,7 +8,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from raytracercore_b200 import RTC_F32, RTC_F64, RTC_OPT_COUNTERS, RTC_OPT_KERNEL_TIMING, RTC_OPT_MAX_PATHS, Context  # noqa: E402
+from raytracercore_b200 import RTC_F32, RTC_F64, RTC_OPT_COUNTERS, RTC_OPT_KERNEL_TIMING, RTC_OPT_MAX_PATHS, RTC_OPT_WAVES, Context  # noqa: E402
 from raytracercore_b200 import _native as N  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -19,6 +19,7 @@ ap.add_argument("--size", type=int, default=0, help="override width=height")
 ap.add_argument("--precision", default="f32")
 ap.add_argument("--counters", action="store_true")
 ap.add_argument("--max-paths", type=int, default=0)
+ap.add_argument("--waves", type=int, default=0, help="wavefronts in flight (RTC_OPT_WAVES); implies no per-kernel timing")
 ap.add_argument("--device-bvh", type=int, default=-1, help="build the tree on the GPU with this search radius (0 = default)")
 a = ap.parse_args()
 sc = bench.make_scene(a.workload)
@@ -47,7 +48,10 @@ else:
 ctx.render(0, a.spp)
 ctx.sync()
 ctx.reset_stats()
-ctx.set_option(RTC_OPT_KERNEL_TIMING, 1)
+if a.waves:
+    ctx.set_option(RTC_OPT_WAVES, a.waves)
+else:
+    ctx.set_option(RTC_OPT_KERNEL_TIMING, 1)
 if a.counters:
     ctx.set_option(RTC_OPT_COUNTERS, 1)
 t = time.time()
