@@ -205,7 +205,7 @@ int rtc_build_bvh_device(rtc_ctx* ctx, int32_t radius, int32_t* rounds);
  * every FullRaytracer.Start(). A baked image belongs to one arithmetic mode. */
 typedef struct rtc_baked rtc_baked;
 int rtc_bake(rtc_ctx* ctx, rtc_baked** out);
-int rtc_upload_baked(rtc_ctx* ctx, const rtc_baked* baked);
+int rtc_upload_baked(rtc_ctx* ctx, const rtc_baked* baked); /* asynchronous; rtc_baked_free waits for uploads still reading the image */
 int64_t rtc_baked_bytes(const rtc_baked* baked);
 void rtc_baked_free(rtc_baked* baked);
 /* Read the current tree back in reference shape (for SceneInspector.cs:226-265 and for the parity oracle). */

@@ -85,7 +85,23 @@ struct rtc_baked {
   char* host = nullptr;
   size_t total = 0;
   bool pinned = false;
+  // the asynchronous uploads that still read this image: one event per stream an upload was issued on (recorded behind the
+  // last copy); the image is not released before they have passed
+  mutable cudaEvent_t in_flight[2] = {nullptr, nullptr};
+  void mark_in_flight(int which, cudaStream_t st) const {
+    if (!in_flight[which] && cudaEventCreateWithFlags(&in_flight[which], cudaEventDisableTiming) != cudaSuccess) {
+      in_flight[which] = nullptr;
+      cudaStreamSynchronize(st);  // no event to wait on later: wait now
+      return;
+    }
+    cudaEventRecord(in_flight[which], st);
+  }
   ~rtc_baked() {
+    for (cudaEvent_t& e : in_flight)
+      if (e) {
+        cudaEventSynchronize(e);
+        cudaEventDestroy(e);
+      }
     if (host) {
       if (pinned) cudaFreeHost(host);
       else std::free(host);
@@ -518,7 +534,9 @@ int upload_baked_image(rtc_ctx* ctx, const rtc_baked* bk) {
         CU(cudaMemcpyAsync(*dst[i], bk->host + bk->off[i], bk->bytes[i], cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_shading, ctx->copy_stream));
     ctx->shading_pending = true;
+    bk->mark_in_flight(1, ctx->copy_stream);
   }
+  if (bk->pinned) bk->mark_in_flight(0, ctx->stream);  // (a pageable image is synchronised below)
   if (bk->bytes[rtc_baked::S_QNODES] == 0 && bk->precision == RTC_F32) {
     // no bounded primitive: the kernel keys on a null qnodes pointer
     CU(cudaStreamSynchronize(ctx->stream));

@@ -10,7 +10,10 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <type_traits>
+#include <utility>
 
 #include "rtc_internal.h"
 
@@ -1938,26 +1941,36 @@ template <typename R>
 cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, bool identity_queue) {
   const size_t smem = Num<R>::is_f64 ? (size_t)sc.q_stack * kTraceThreads * (4 + sizeof(R))
                                      : (size_t)sc.q_stack * kTraceThreads * sizeof(uint2) + kQ8StateWords * kTraceThreads * sizeof(float);
-  // resident CTAs per SM for the (device, stack size) last seen (persistent grid = all of them); function attributes are
-  // per device, so a change of device re-applies them
-  static thread_local size_t per_sm_smem = ~(size_t)0;
-  static thread_local int per_sm = 1, per_sm_dev = -1;
+  // Function attributes and occupancy are per (device, kernel) for the whole process, whatever thread launches: the largest
+  // dynamic shared-memory size asked for so far is kept per device (raised, never lowered: a smaller launch is always legal
+  // under a larger limit) and the resident-CTA count per (device, size), under one mutex.
+  static std::mutex mu;
+  static std::map<int, size_t> limit_set;
+  static std::map<std::pair<int, size_t>, int> resident;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (smem != per_sm_smem || dev != per_sm_dev) {
-    per_sm_dev = dev;
-    if constexpr (Num<R>::is_f64) {  // deep trees need more than the default 48 KB of dynamic shared memory
-      cudaFuncSetAttribute(k_trace<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_trace<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    } else if (smem > 48 * 1024) {
-      cudaFuncSetAttribute(k_trace_q8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_trace_q8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 1;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    size_t& lim = limit_set[dev];
+    if (smem > lim && (Num<R>::is_f64 || smem > 48 * 1024)) {  // beyond the default 48 KB of dynamic shared memory: opt in
+      cudaError_t e;
+      if constexpr (Num<R>::is_f64) {
+        e = cudaFuncSetAttribute(k_trace<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      } else {
+        e = cudaFuncSetAttribute(k_trace_q8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_trace_q8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      }
+      if (e != cudaSuccess) return e;  // (a tree too deep for the SM's shared memory surfaces here, through fail())
+      lim = smem;
     }
-    per_sm = trace_blocks_per_sm(smem);
-    if (const char* cap = std::getenv("RTC_TRACE_BLOCKS_PER_SM"))  // tuning aid: fewer resident CTAs than fit
-      per_sm = std::max(1, std::min(per_sm, std::atoi(cap)));
-    per_sm_smem = smem;
+    auto it = resident.find({dev, smem});
+    if (it == resident.end()) it = resident.emplace(std::make_pair(dev, smem), trace_blocks_per_sm(smem)).first;
+    per_sm = it->second;
   }
+  if (const char* cap = std::getenv("RTC_TRACE_BLOCKS_PER_SM"))  // tuning aid: fewer resident CTAs than fit
+    per_sm = std::max(1, std::min(per_sm, std::atoi(cap)));
   int grid = cfg.sm_count * per_sm;
   TraceIO<R> io;
   io.dir = pv.dir;

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <fstream>
+#include <limits>
 #include <sstream>
 
 #include "scene.h"
@@ -94,23 +95,64 @@ struct Params {
   }
 };
 
-double ParseDbl(const std::string& s) {  // double.Parse(str, InvariantCulture), SceneLoader.cs:50-53
-  if (s.empty()) throw std::invalid_argument("Input string was not in a correct format.");
-  for (char c : s)
-    if (c == 'x' || c == 'X' || c == 'p' || c == 'P') throw std::invalid_argument("Input string was not in a correct format.");
-  errno = 0;
-  char* end = nullptr;
-  double v = std::strtod(s.c_str(), &end);
-  if (end == s.c_str() || *end != '\0') throw std::invalid_argument("Input string was not in a correct format.");
-  return v;
+// double.Parse(str, InvariantCulture), SceneLoader.cs:50-53. NumberStyles.Float | AllowThousands: [sign] digits with optional
+// group separators, an optional fraction, an optional exponent -- or one of the symbols Infinity, -Infinity, NaN (matched
+// without regard to case, as .NET Core 3.0+ does). strtod alone would also take "inf", "nan(...)", hex floats and a bare
+// "infinity" prefix, which the reference rejects with a FormatException -> LoaderException.
+double ParseDbl(const std::string& s) {
+  const auto bad = []() { return std::invalid_argument("Input string was not in a correct format."); };
+  if (s.empty()) throw bad();
+  size_t i = 0;
+  bool neg = false;
+  if (s[i] == '+' || s[i] == '-') neg = s[i++] == '-';
+  auto ieq = [&](const char* w) {
+    size_t k = 0;
+    for (; w[k]; k++)
+      if (i + k >= s.size() || std::tolower((unsigned char)s[i + k]) != w[k]) return false;
+    return i + k == s.size();
+  };
+  if (ieq("infinity")) return neg ? -std::numeric_limits<double>::infinity() : std::numeric_limits<double>::infinity();
+  if (ieq("nan")) return std::numeric_limits<double>::quiet_NaN();
+  std::string digits;  // the same number without group separators, for strtod
+  if (neg) digits.push_back('-');
+  size_t n_int = 0, n_frac = 0;
+  while (i < s.size() && (std::isdigit((unsigned char)s[i]) || s[i] == ',')) {
+    if (s[i] != ',') {
+      digits.push_back(s[i]);
+      n_int++;
+    }
+    i++;
+  }
+  if (i < s.size() && s[i] == '.') {
+    digits.push_back(s[i++]);
+    while (i < s.size() && std::isdigit((unsigned char)s[i])) {
+      digits.push_back(s[i++]);
+      n_frac++;
+    }
+  }
+  if (n_int + n_frac == 0) throw bad();
+  if (i < s.size() && (s[i] == 'e' || s[i] == 'E')) {
+    digits.push_back(s[i++]);
+    if (i < s.size() && (s[i] == '+' || s[i] == '-')) digits.push_back(s[i++]);
+    size_t n_exp = 0;
+    while (i < s.size() && std::isdigit((unsigned char)s[i])) {
+      digits.push_back(s[i++]);
+      n_exp++;
+    }
+    if (n_exp == 0) throw bad();
+  }
+  if (i != s.size()) throw bad();
+  return std::strtod(digits.c_str(), nullptr);
 }
 
-int ParseInt(const std::string& s) {  // int.Parse, SceneLoader.cs:60-63
+int ParseInt(const std::string& s) {  // int.Parse, SceneLoader.cs:60-63 (NumberStyles.Integer: [sign] digits)
   if (s.empty()) throw std::invalid_argument("Input string was not in a correct format.");
+  size_t i = (s[0] == '+' || s[0] == '-') ? 1 : 0;
+  if (i == s.size()) throw std::invalid_argument("Input string was not in a correct format.");
+  for (size_t k = i; k < s.size(); k++)
+    if (!std::isdigit((unsigned char)s[k])) throw std::invalid_argument("Input string was not in a correct format.");
   errno = 0;
-  char* end = nullptr;
-  long v = std::strtol(s.c_str(), &end, 10);
-  if (end == s.c_str() || *end != '\0') throw std::invalid_argument("Input string was not in a correct format.");
+  long long v = std::strtoll(s.c_str(), nullptr, 10);
   if (errno == ERANGE || v > INT_MAX || v < INT_MIN) throw std::overflow_error("Value was either too large or too small for an Int32.");
   return (int)v;
 }

@@ -178,11 +178,28 @@ def test_bare_cube_creates_nothing_and_instance_draws_faces():
     ("poptransform\npoptransform\n", "poptransform", 2),       # stack underflow
     ("cube 0 0 0 1 1 1 only +w\n", "cube", 1),
     ("size 99999999999 1\n", "size", 1),                       # OverflowException
+    ("shininess inf\n", "shininess", 1),                       # spellings strtod takes but double.Parse does not
+    ("shininess nan(1)\n", "shininess", 1),
+    ("shininess 0x1p3\n", "shininess", 1),
+    ("shininess 1e\n", "shininess", 1),
+    ("shininess .\n", "shininess", 1),
+    ("size 0x10 16\n", "size", 1),
+    ("size 1.0 16\n", "size", 1),
 ])
 def test_loader_exception_names_command_and_line(text, cmd, line):
     with pytest.raises(LoaderException) as e:
         Scene.from_string(text)
     assert "command %s on line %d" % (cmd, line) in str(e.value)
+
+
+def test_number_grammar_is_dotnets():
+    """double.Parse(InvariantCulture): Infinity / NaN symbols, group separators, exponents, a leading '+'."""
+    sc = Scene.from_string("shininess Infinity\nrefraction 1 1 1 +1.5e0\ndiffuse .5 5. 1E+1\nsphere 0 0 0 1\n")
+    m = sc.arrays()["material"][0]
+    assert np.isinf(m[13]) and m[12] == 1.5 and list(m[3:6]) == [0.5, 5.0, 10.0]
+    sc = Scene.from_string("shininess -infinity\nemission NaN 0 0\nsphere 0 0 0 1\n")
+    m = sc.arrays()["material"][0]
+    assert m[13] == -np.inf and np.isnan(m[0])
 
 
 def test_line_format_errors_and_missing_file():
