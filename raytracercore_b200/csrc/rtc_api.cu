@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../host/scene.h"
+#include "prepare_common.h"
 #include "rtc_internal.h"
 
 using namespace rtc;
@@ -826,20 +827,9 @@ int build_device_scene(rtc_ctx* ctx) {
       }
     });
     // a binary node with bounded leaves on one side only is transparent
-    auto resolve = [&](int32_t i) -> int32_t {
-      while (nodes[i].prim < 0) {
-        int32_t l = nodes[i].left, r = nodes[i].right;
-        if (nf[l] == 0) i = r;
-        else if (nf[r] == 0) i = l;
-        else break;
-      }
-      return i;
-    };
+    auto resolve = [&](int32_t i) -> int32_t { return prep::resolve(nodes.data(), nf.data(), i); };
     pt.mark("validate + boxes");
-    // Optimal collapse (after Ylitie, Karras & Laine 2017, sec. 3): T(m, i) = least total surface area of the wide nodes
-    // needed below binary node m when m's subtree may occupy at most i child slots of its parent wide node. A leaf costs
-    // nothing; an inner node either becomes a wide node itself (its area + its two sides spread over 8 slots) or hands
-    // its slots on to its two sides. Evaluated children-first; cut[m][j] is the left side's share when j slots are split.
+    // Optimal collapse (prepare_common.h: dp_node), children first; cut[m][j] is the left side's share when j slots are split.
     std::vector<float> T((size_t)nn * 8, 0.0f);
     std::vector<uint8_t> cut((size_t)nn * 9, 0);
     postorder_parallel(nodes, ctx->root, [&](int32_t i) {
@@ -847,54 +837,10 @@ int build_device_scene(rtc_ctx* ctx) {
       if (nd.prim >= 0 || nf[i] == 0) return;
       if (nf[nd.left] == 0 || nf[nd.right] == 0) return;  // transparent: resolve() skips it
       const int32_t l = resolve(nd.left), r = resolve(nd.right);
-      const float* Tl = &T[(size_t)l * 8];
-      const float* Tr = &T[(size_t)r * 8];
-      float D[9];
-      for (int j = 2; j <= 8; j++) {
-        float bestv = std::numeric_limits<float>::infinity();
-        int bestk = 1;
-        for (int k = 1; k < j; k++) {
-          const float v = Tl[std::min(k, 7)] + Tr[std::min(j - k, 7)];
-          if (v < bestv) {
-            bestv = v;
-            bestk = k;
-          }
-        }
-        D[j] = bestv;
-        cut[(size_t)i * 9 + j] = (uint8_t)bestk;
-      }
-      float* Ti = &T[(size_t)i * 8];
-      const float as_node = (float)area(&fmin[(size_t)i * 3], &fmax[(size_t)i * 3]) + D[8];
-      Ti[1] = as_node;
-      for (int j = 2; j <= 7; j++) Ti[j] = std::min(as_node, D[j]);
+      prep::dp_node(&T[(size_t)l * 8], &T[(size_t)r * 8], prep::box_area(&fmin[(size_t)i * 3], &fmax[(size_t)i * 3]), &T[(size_t)i * 8],
+                    &cut[(size_t)i * 9]);
     });
-    // fills kids[] with the children of the wide node rooted at binary node m
-    auto gather_children = [&](int32_t m, int32_t* kids, int& nk) {
-      struct It {
-        int32_t node;
-        int slots;
-        bool force_split;
-      };
-      It stack_[32];
-      int sp_ = 0;
-      stack_[sp_++] = {m, 8, true};
-      while (sp_ > 0) {
-        It it = stack_[--sp_];
-        const rtc_bvh_node& nd = nodes[it.node];
-        if (nd.prim >= 0) {
-          kids[nk++] = it.node;
-          continue;
-        }
-        const float* Ti = &T[(size_t)it.node * 8];
-        if (!it.force_split && (it.slots == 1 || Ti[std::min(it.slots, 7)] >= Ti[1])) {
-          kids[nk++] = it.node;  // stays a wide node of its own
-          continue;
-        }
-        const int k = cut[(size_t)it.node * 9 + it.slots];
-        stack_[sp_++] = {resolve(nd.right), it.slots - k, false};
-        stack_[sp_++] = {resolve(nd.left), k, false};
-      }
-    };
+    const prep::TreeView tv{nodes.data(), nf.data(), fmin.data(), fmax.data(), T.data(), cut.data()};
     pt.mark("collapse DP");
     const int32_t n_bounded = nf[ctx->root];
     int32_t next_slot = 0;
@@ -924,109 +870,13 @@ int build_device_scene(rtc_ctx* ctx) {
         parallel_for(lv_begin, lv_end, 2048, [&](size_t qi) {
           const QWork wk = queue[qi];
           Emit& em = level[qi - lv_begin];
-          int32_t* kids = em.kids;
-          int nk = 0;
           if (nodes[wk.bnode].prim >= 0) {
-            kids[nk++] = wk.bnode;  // tree of a single bounded primitive
+            em.kids[0] = wk.bnode;  // tree of a single bounded primitive
+            em.nk = 1;
           } else {
-            gather_children(wk.bnode, kids, nk);
+            em.nk = prep::gather_children(tv, wk.bnode, em.kids);
           }
-          em.nk = nk;
-          // node box, grid origin and per-axis power-of-two step
-          double lo[3], hi[3];
-          for (int a = 0; a < 3; a++) {
-            lo[a] = std::numeric_limits<double>::infinity();
-            hi[a] = -std::numeric_limits<double>::infinity();
-            for (int c = 0; c < nk; c++) {
-              lo[a] = std::min(lo[a], fmin[(size_t)kids[c] * 3 + a]);
-              hi[a] = std::max(hi[a], fmax[(size_t)kids[c] * 3 + a]);
-            }
-          }
-          CNode& cn = em.cn;
-          std::memset(&cn, 0, sizeof(cn));
-          float p[3];
-          int ex[3];
-          double step[3];
-          for (int a = 0; a < 3; a++) {
-            // grid: origin one step below the box minimum (so the one-step padding of the children never clamps at 0),
-            // step = smallest power of two that spans the box in 250 steps
-            double ext = hi[a] - lo[a];
-            int e = ext > 0 ? (int)std::ceil(std::log2(ext / 250.0)) : -100;
-            e = std::min(std::max(e, -120), 120);
-            while (std::ldexp(1.0, e) * 250.0 < ext) e++;
-            p[a] = round_down<float>(lo[a] - std::ldexp(1.0, e));
-            while (std::ldexp(1.0, e) * 253.0 < hi[a] - (double)p[a]) {
-              e++;
-              p[a] = round_down<float>(lo[a] - std::ldexp(1.0, e));
-            }
-            ex[a] = e;
-            step[a] = std::ldexp(1.0, e);
-          }
-          cn.px = p[0];
-          cn.py = p[1];
-          cn.pz = p[2];
-          // slot assignment: child i goes to the free slot whose octant signs best match its offset from the centre
-          int slot_of[8];
-          {
-            double ctr[3];
-            for (int a = 0; a < 3; a++) ctr[a] = 0.5 * (lo[a] + hi[a]);
-            double cost[8][8];
-            for (int c = 0; c < nk; c++)
-              for (int s2 = 0; s2 < 8; s2++) {
-                double v = 0;
-                for (int a = 0; a < 3; a++) {
-                  double off = 0.5 * (fmin[(size_t)kids[c] * 3 + a] + fmax[(size_t)kids[c] * 3 + a]) - ctr[a];
-                  v += ((s2 >> a) & 1) ? off : -off;
-                }
-                cost[c][s2] = v;
-              }
-            bool cu[8] = {false, false, false, false, false, false, false, false}, su[8] = {false, false, false, false, false, false, false, false};
-            for (int it = 0; it < nk; it++) {
-              int bc = -1, bs = -1;
-              double bv = -std::numeric_limits<double>::infinity();
-              for (int c = 0; c < nk; c++)
-                if (!cu[c])
-                  for (int s2 = 0; s2 < 8; s2++)
-                    if (!su[s2] && cost[c][s2] > bv) {
-                      bv = cost[c][s2];
-                      bc = c;
-                      bs = s2;
-                    }
-              cu[bc] = true;
-              su[bs] = true;
-              slot_of[bc] = bs;
-            }
-          }
-          for (int s2 = 0; s2 < 8; s2++) em.child_in_slot[s2] = -1;
-          for (int c = 0; c < nk; c++) em.child_in_slot[slot_of[c]] = (int8_t)c;
-          uint32_t imask = 0, lmask = 0;
-          uint8_t qb[6][8];
-          std::memset(qb, 0, sizeof(qb));
-          for (int s2 = 0; s2 < 8; s2++) {
-            int c = em.child_in_slot[s2];
-            if (c < 0) {
-              for (int a = 0; a < 3; a++) {  // empty slot: inverted box, never hit
-                qb[a][s2] = 255;
-                qb[3 + a][s2] = 0;
-              }
-              continue;
-            }
-            int32_t k = kids[c];
-            for (int a = 0; a < 3; a++) {
-              double ql = std::floor((fmin[(size_t)k * 3 + a] - (double)p[a]) / step[a]) - 1.0;
-              double qh = std::ceil((fmax[(size_t)k * 3 + a] - (double)p[a]) / step[a]) + 1.0;
-              qb[a][s2] = (uint8_t)std::min(255.0, std::max(0.0, ql));
-              qb[3 + a][s2] = (uint8_t)std::min(255.0, std::max(0.0, qh));
-            }
-            if (nodes[k].prim >= 0)
-              lmask |= 1u << s2;
-            else
-              imask |= 1u << s2;
-          }
-          cn.e_imask = (uint32_t)(ex[0] + 127) | ((uint32_t)(ex[1] + 127) << 8) | ((uint32_t)(ex[2] + 127) << 16) | (imask << 24);
-          cn.lmask = lmask;
-          for (int r = 0; r < 6; r++)
-            for (int s2 = 0; s2 < 8; s2++) cn.q[r * 2 + (s2 >> 2)] |= (uint32_t)qb[r][s2] << (8 * (s2 & 3));
+          prep::make_cnode(tv, em.kids, em.nk, em.cn, em.child_in_slot);  // everything but the two base indices
         });
         for (size_t qi = lv_begin; qi < lv_end; qi++) {
           const int32_t depth = queue[qi].depth;
