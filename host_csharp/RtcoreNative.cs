@@ -72,11 +72,20 @@ namespace RaytracerCore.Raytracing.Gpu
 		public ulong NodesVisited, PrimsTested, NodeSteps, LeafSteps;
 	}
 
+	/// <summary>rtc_prepare_stats: phases of Scene.Prepare on the device (rtc_prepare_device).</summary>
+	[StructLayout(LayoutKind.Sequential)]
+	public struct RtcPrepareStats
+	{
+		public double BoxesMs, BuildMs, FlattenMs, TotalMs;
+		public int BuildLevels, WideDepth, NWideNodes, NBounded;
+	}
+
 	public static unsafe class RtcoreNative
 	{
 		const string Lib = "rtcore_b200";   // librtcore_b200.so / rtcore_b200.dll
 
 		public const int F32 = 0, F64 = 1;
+		public const int BuilderSah = 0, BuilderPloc = 1;
 		public const int KindTriangle = 0, KindSphere = 1, KindPlane = 2;
 		public const int FlagMirror = 1, FlagTwoSided = 2, FlagInvert = 4, FlagTransformed = 8, FlagVNormals = 16;
 		public const int OverlayPrimitives = 0, OverlayBoundingVolumes = 1;
@@ -96,6 +105,8 @@ namespace RaytracerCore.Raytracing.Gpu
 		[DllImport(Lib)] public static extern int rtc_upload_baked(IntPtr ctx, IntPtr baked);
 		[DllImport(Lib)] public static extern long rtc_baked_bytes(IntPtr baked);
 		[DllImport(Lib)] public static extern void rtc_baked_free(IntPtr baked);
+		[DllImport(Lib)] public static extern int rtc_baked_segment(IntPtr baked, int segment, out IntPtr data, out long bytes);
+		[DllImport(Lib)] public static extern int rtc_prepare_device(IntPtr ctx, int builder, int radius, RtcPrepareStats* stats);
 		[DllImport(Lib)] public static extern int rtc_get_bvh_size(IntPtr ctx, out int nNodes, out int root);
 		[DllImport(Lib)] public static extern int rtc_get_bvh(IntPtr ctx, int capacity, RtcBvhNode* nodes);
 		[DllImport(Lib)] public static extern int rtc_set_camera(IntPtr ctx, RtcCamera* camera);

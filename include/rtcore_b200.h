@@ -200,6 +200,23 @@ int rtc_build_bvh(rtc_ctx* ctx);
  * exact f64 boxes; rtc_get_bvh returns the tree in the reference's shape. rounds (may be NULL) receives the number of
  * clustering rounds. */
 int rtc_build_bvh_device(rtc_ctx* ctx, int32_t radius, int32_t* rounds);
+/* Scene.Prepare (Scene.cs:39-49) wholly on the device: the tree is built there -- RTC_BUILDER_SAH: the binned-SAH tree of
+ * rtc_build_bvh, node for node; RTC_BUILDER_PLOC: the clustering of rtc_build_bvh_device with `radius` -- and, in RTC_F32 mode,
+ * collapsed, quantised and packed into the device layout there too, byte for byte what rtc_build_bvh / rtc_upload_bvh produce
+ * on the host. Nothing comes back over PCIe: rtc_get_bvh and rtc_bake fetch the tree / the image from the device when asked.
+ * RTC_F64 mode (the parity mode) builds on the device and flattens on the host. stats may be NULL. */
+enum { RTC_BUILDER_SAH = 0, RTC_BUILDER_PLOC = 1 };
+typedef struct rtc_prepare_stats {
+  double boxes_ms;    /* leaf boxes (AABB.CreateFromBounded) on the host threads                     */
+  double build_ms;    /* box upload + tree construction                                               */
+  double flatten_ms;  /* collapse + quantisation + records (includes waiting for the scene arrays)  */
+  double total_ms;
+  int32_t build_levels; /* SAH: tree levels; PLOC: clustering rounds */
+  int32_t wide_depth;   /* depth of the 8-wide tree (RTC_F32)         */
+  int32_t n_wide_nodes;
+  int32_t n_bounded;
+} rtc_prepare_stats;
+int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepare_stats* stats);
 /* Scene.Prepare caches the accelerator on the host (Scene.cs:39-49); the equivalent here is a host-resident image of
  * the device layout (pinned memory), made once from the current scene + BVH and re-uploaded with plain H2D copies at
  * every FullRaytracer.Start(). A baked image belongs to one arithmetic mode. */
@@ -207,6 +224,10 @@ typedef struct rtc_baked rtc_baked;
 int rtc_bake(rtc_ctx* ctx, rtc_baked** out);
 int rtc_upload_baked(rtc_ctx* ctx, const rtc_baked* baked); /* asynchronous; rtc_baked_free waits for uploads still reading the image */
 int64_t rtc_baked_bytes(const rtc_baked* baked);
+/* One of the RTC_BAKED_SEGMENTS arrays of the image (read-only view into the baked image's own memory, valid until
+ * rtc_baked_free): what a host that caches prepared scenes on disk would write out, and what the tests compare. */
+enum { RTC_BAKED_SEGMENTS = 10 };
+int rtc_baked_segment(const rtc_baked* baked, int32_t segment, const void** data, int64_t* bytes);
 void rtc_baked_free(rtc_baked* baked);
 /* Read the current tree back in reference shape (for SceneInspector.cs:226-265 and for the parity oracle). */
 int rtc_get_bvh_size(rtc_ctx* ctx, int32_t* n_nodes, int32_t* root);

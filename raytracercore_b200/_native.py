@@ -21,6 +21,9 @@ RTC_CAMERA_FRUSTUM, RTC_CAMERA_ORTHO = 0, 1
 RTC_GEOM_STRIDE, RTC_MATERIAL_STRIDE, RTC_XFORM_STRIDE = 12, 14, 48
 RTC_K_RAYGEN, RTC_K_TRACE, RTC_K_SHADE, RTC_K_COMPACT, RTC_K_ACCUMULATE, RTC_K_COUNT = 0, 1, 2, 3, 4, 5
 RTC_OPT_KERNEL_TIMING, RTC_OPT_COUNTERS, RTC_OPT_MAX_PATHS, RTC_OPT_WAVES = 1, 2, 3, 4
+RTC_BUILDER_SAH, RTC_BUILDER_PLOC = 0, 1
+RTC_BAKED_SEGMENTS = 10
+BAKED_SEGMENT_NAMES = ("nodes", "qnodes", "unbounded", "prims", "mats", "xforms", "aux", "prim_id", "id_to_slot", "sgeom")
 KERNEL_NAMES = ("raygen", "trace", "shade", "compact", "accumulate")
 BOUNCE_TYPES = ("Skipped", "Diffuse", "Specular", "SpecularFail", "Transmitted", "Emission", "PureBlack",
                 "RecursionComplete", "Missed", "Debug")
@@ -47,6 +50,11 @@ class Camera(C.Structure):
 class Params(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("recursion", C.c_int32), ("debug_geom", C.c_int32),
                 ("ambient", C.c_double * 3), ("air_ior", C.c_double), ("seed", C.c_uint64)]
+
+
+class PrepareStats(C.Structure):
+    _fields_ = [("boxes_ms", C.c_double), ("build_ms", C.c_double), ("flatten_ms", C.c_double), ("total_ms", C.c_double),
+                ("build_levels", C.c_int32), ("wide_depth", C.c_int32), ("n_wide_nodes", C.c_int32), ("n_bounded", C.c_int32)]
 
 
 class Ray(C.Structure):
@@ -95,6 +103,8 @@ SIGNATURES = {
     "rtc_upload_baked": (C.c_int, [_P, _P]),
     "rtc_baked_bytes": (C.c_int64, [_P]),
     "rtc_baked_free": (None, [_P]),
+    "rtc_baked_segment": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "rtc_prepare_device": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(PrepareStats)]),
     "rtc_get_bvh_size": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rtc_get_bvh": (C.c_int, [_P, C.c_int32, C.POINTER(BvhNode)]),
     "rtc_set_camera": (C.c_int, [_P, C.POINTER(Camera)]),

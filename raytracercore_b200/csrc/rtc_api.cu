@@ -121,6 +121,24 @@ struct rtc_baked {
   }
 };
 
+// allocator whose construct() leaves trivially-constructible elements uninitialised: resize() of the two large scene arrays
+// must not write 200 MB of zeros that the copy behind it overwrites
+template <typename T>
+struct NoInitAlloc : std::allocator<T> {
+  template <typename U>
+  struct rebind {
+    using other = NoInitAlloc<U>;
+  };
+  template <typename U>
+  void construct(U* p) noexcept {
+    ::new ((void*)p) U;
+  }
+  template <typename U, typename... A>
+  void construct(U* p, A&&... a) {
+    ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
+
 struct rtc_ctx {
   int device = 0;
   int precision = RTC_F32;
@@ -132,7 +150,8 @@ struct rtc_ctx {
   // host copy of the scene as handed over (f64)
   int32_t n_prims = 0, n_xforms = 0;
   std::vector<uint8_t> kind, flags;
-  std::vector<double> geom, xforms, material;
+  std::vector<double, NoInitAlloc<double>> geom, material;
+  std::vector<double> xforms;
   std::vector<int32_t> xform;
   std::vector<rtc_bvh_node> nodes;
   int32_t root = -1;
@@ -151,7 +170,16 @@ struct rtc_ctx {
   int bvh_depth = 0;
   size_t seg_cap[rtc_baked::S_COUNT] = {0};  // device capacity per scene segment (buffers are reused across uploads)
   size_t seg_bytes[rtc_baked::S_COUNT] = {0};  // bytes of each segment in use by the current device scene
-  rtc_baked* baked = nullptr;               // image of the current device scene
+  rtc_baked* baked = nullptr;               // image of the current device scene (null after rtc_prepare_device / rtc_bcast_scene:
+                                            // rtc_bake then reads the segments back from the device)
+  // rtc_prepare_device: pinned staging ring (host threads convert into it, the copy engine drains it) and a small pinned
+  // read-back block for the level-synchronous passes
+  char* h_ring[2] = {nullptr, nullptr};
+  cudaEvent_t ev_ring[2] = {nullptr, nullptr};
+  bool ring_busy[2] = {false, false};
+  int32_t* h_pin = nullptr;
+  rtc_bvh_node* d_bnodes = nullptr;         // rtc_prepare_device: the reference-shaped tree stays on the device; `nodes` is
+  int32_t n_bnodes = 0;                     // filled from it when rtc_get_bvh / the box-count overlay ask
 
   // path pool
   int64_t max_paths = 1 << 25;
@@ -340,6 +368,8 @@ void free_scene_device(rtc_ctx* c) {
   free_dev(c->d_sgeom);
   free_dev(c->d_qnodes);
   free_dev_t(c->d_unbounded);
+  free_dev_t(c->d_bnodes);
+  c->n_bnodes = 0;
   c->n_unbounded = 0;
   for (size_t& v : c->seg_cap) v = 0;
 }
@@ -616,6 +646,74 @@ void postorder_parallel(const std::vector<rtc_bvh_node>& nodes, int32_t root, F&
     }
   });
   for (size_t k = top.size(); k-- > 0;) post(top[k]);  // (breadth-first order reversed: children first)
+}
+
+void drop_device_tree(rtc_ctx* ctx) {
+  if (!ctx->d_bnodes) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_dev_t(ctx->d_bnodes);
+  ctx->n_bnodes = 0;
+}
+
+// the reference-shaped tree on the host, fetched from the device after rtc_prepare_device
+int ensure_host_nodes(rtc_ctx* ctx) {
+  if (!ctx->nodes.empty() || !ctx->d_bnodes) return RTC_OK;
+  cudaSetDevice(ctx->device);
+  ctx->nodes.resize((size_t)ctx->n_bnodes);
+  CU(cudaMemcpyAsync(ctx->nodes.data(), ctx->d_bnodes, (size_t)ctx->n_bnodes * sizeof(rtc_bvh_node), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RTC_OK;
+}
+
+// device buffer of scene segment `seg` with room for `bytes` (buffers are reused across scenes)
+int ensure_seg(rtc_ctx* ctx, int seg, size_t bytes) {
+  void** dst[rtc_baked::S_COUNT] = {&ctx->d_nodes, &ctx->d_qnodes, (void**)&ctx->d_unbounded, &ctx->d_prims, &ctx->d_mats,
+                                    &ctx->d_xforms, (void**)&ctx->d_aux, (void**)&ctx->d_prim_id, (void**)&ctx->d_id_to_slot,
+                                    &ctx->d_sgeom};
+  const size_t need = std::max<size_t>(bytes, 16);
+  if (ctx->seg_cap[seg] < need || !*dst[seg]) {
+    if (*dst[seg]) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
+      cudaFree(*dst[seg]);
+      *dst[seg] = nullptr;
+    }
+    CU(cudaMalloc(dst[seg], need));
+    ctx->seg_cap[seg] = need;
+  }
+  return RTC_OK;
+}
+
+constexpr size_t kRingBytes = (size_t)8 << 20;
+
+int ensure_stage_ring(rtc_ctx* ctx) {
+  if (ctx->h_pin) return RTC_OK;
+  for (int i = 0; i < 2; i++) {
+    CU(cudaMallocHost((void**)&ctx->h_ring[i], kRingBytes));
+    CU(cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
+  }
+  CU(cudaMallocHost((void**)&ctx->h_pin, 64));
+  return RTC_OK;
+}
+
+// n items of item_bytes each: fill(i, dst) writes item i; chunks of the pinned ring are filled on the host threads and copied
+// to d_dst on `stream` while the next chunk is being filled. One caller at a time.
+template <typename F>
+int staged_upload(rtc_ctx* ctx, cudaStream_t stream, size_t n, size_t item_bytes, char* d_dst, F&& fill) {
+  const size_t per = kRingBytes / item_bytes;
+  size_t k = 0;
+  for (size_t first = 0; first < n; first += per, k++) {
+    const int slot = (int)(k & 1);
+    if (ctx->ring_busy[slot]) CU(cudaEventSynchronize(ctx->ev_ring[slot]));
+    const size_t cnt = std::min(per, n - first);
+    char* base = ctx->h_ring[slot];
+    parallel_for(0, cnt, 2048, [&](size_t i) { fill(first + i, base + i * item_bytes); });
+    CU(cudaMemcpyAsync(d_dst + first * item_bytes, base, cnt * item_bytes, cudaMemcpyHostToDevice, stream));
+    CU(cudaEventRecord(ctx->ev_ring[slot], stream));
+    ctx->ring_busy[slot] = true;
+  }
+  return RTC_OK;
 }
 
 // RTC_B200_VERBOSE: wall-clock of the phases of build_device_scene
@@ -1369,6 +1467,11 @@ void rtc_destroy(rtc_ctx* ctx) {
     cudaEventDestroy(ctx->ev_ui_done);
     cudaFreeHost(ctx->h_pixel);
   }
+  for (int i = 0; i < 2; i++) {
+    if (ctx->h_ring[i]) cudaFreeHost(ctx->h_ring[i]);
+    if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
+  }
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->h_argb) cudaFreeHost(ctx->h_argb);
   free_dev_t(ctx->d_argb);
   free_dev(ctx->d_scratch);
@@ -1434,8 +1537,21 @@ int rtc_upload_scene(rtc_ctx* ctx, const rtc_scene_desc* s) {
   ctx->n_xforms = s->n_xforms;
   ctx->kind.assign(s->kind, s->kind + n);
   ctx->flags.assign(s->flags, s->flags + n);
-  ctx->geom.assign(s->geom, s->geom + n * RTC_GEOM_STRIDE);
-  ctx->material.assign(s->material, s->material + n * RTC_MATERIAL_STRIDE);
+  ctx->geom.resize(n * RTC_GEOM_STRIDE);  // (no value-initialisation: NoInitAlloc)
+  ctx->material.resize(n * RTC_MATERIAL_STRIDE);
+  {  // the two large arrays are copied in 4 MB pieces on the host threads
+    struct Piece {
+      char* dst;
+      const char* src;
+      size_t len;
+    };
+    std::vector<Piece> pieces;
+    const size_t kPiece = (size_t)4 << 20;
+    const size_t gb = n * RTC_GEOM_STRIDE * sizeof(double), mb = n * RTC_MATERIAL_STRIDE * sizeof(double);
+    for (size_t o = 0; o < gb; o += kPiece) pieces.push_back({(char*)ctx->geom.data() + o, (const char*)s->geom + o, std::min(kPiece, gb - o)});
+    for (size_t o = 0; o < mb; o += kPiece) pieces.push_back({(char*)ctx->material.data() + o, (const char*)s->material + o, std::min(kPiece, mb - o)});
+    parallel_for(0, pieces.size(), 2, [&](size_t k) { std::memcpy(pieces[k].dst, pieces[k].src, pieces[k].len); });
+  }
   if (s->xform)
     ctx->xform.assign(s->xform, s->xform + n);
   else
@@ -1448,11 +1564,13 @@ int rtc_upload_scene(rtc_ctx* ctx, const rtc_scene_desc* s) {
   ctx->bvh_set = false;  // Scene.AddPrimitive -> ResetAccelerator (Scene.cs:58-63)
   ctx->nodes.clear();
   ctx->root = -1;
+  drop_device_tree(ctx);
   return RTC_OK;
 }
 
 static int finish_bvh(rtc_ctx* ctx) {
   cudaSetDevice(ctx->device);
+  drop_device_tree(ctx);  // (the host tree in ctx->nodes is the current one)
   int rc = ctx->precision == RTC_F64 ? build_device_scene<double>(ctx) : build_device_scene<float>(ctx);
   ctx->bvh_set = rc == RTC_OK;
   return rc;
@@ -1568,11 +1686,369 @@ int rtc_build_bvh_device(rtc_ctx* ctx, int32_t radius, int32_t* rounds_out) {
   return finish_bvh(ctx);
 }
 
+int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepare_stats* stats) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!ctx->scene_set || (int32_t)ctx->kind.size() != ctx->n_prims) return fail(ctx, RTC_ERR_STATE, "upload the scene before preparing it");
+  if (ctx->n_prims == 0) return fail(ctx, RTC_ERR_INVALID, "scene has no primitives");
+  if (builder != RTC_BUILDER_SAH && builder != RTC_BUILDER_PLOC) return fail(ctx, RTC_ERR_INVALID, "unknown builder");
+  if (ctx->n_prims > (int32_t)REF_SLOT_MASK) return fail(ctx, RTC_ERR_UNSUPPORTED, "more than 2^26-1 primitives");
+  if (radius <= 0) radius = 16;
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  auto ms_since = [](clk::time_point a) { return std::chrono::duration<double, std::milli>(clk::now() - a).count(); };
+  rtc_prepare_stats st;
+  std::memset(&st, 0, sizeof(st));
+  cudaSetDevice(ctx->device);
+  const int32_t n = ctx->n_prims;
+  const bool f32 = ctx->precision == RTC_F32;
+  int rc = wait_shading_upload(ctx);
+  if (rc) return rc;
+  if ((rc = ensure_copy_stream(ctx)) || (rc = ensure_stage_ring(ctx))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  drop_device_tree(ctx);
+  ctx->nodes.clear();
+  ctx->root = -1;
+  ctx->bvh_set = false;
+  rtc_scene_desc d;
+  d.n_prims = n;
+  d.n_xforms = ctx->n_xforms;
+  d.kind = ctx->kind.data();
+  d.flags = ctx->flags.data();
+  d.geom = ctx->geom.data();
+  d.xform = ctx->xform.data();
+  d.xforms = ctx->xforms.empty() ? nullptr : ctx->xforms.data();
+  d.material = ctx->material.data();
+
+  // One device allocation for everything this call needs beside the scene itself: the boxes, the staged records, the slot
+  // table, and the work arrays of the builder and of the flatten (which run one after the other and share their part).
+  const size_t nz = (size_t)n;
+  const int32_t nn_max = 2 * n;  // (2m - 1 + 2 (n - m) <= 2n)
+  const size_t fixed_bytes = nz * 6 * sizeof(double) * 2 + nz * sizeof(int32_t) * 2 + (f32 ? nz * sizeof(StagedPrim) : 0) + 16 * 256;
+  const size_t work_bytes = std::max(build_bvh_sah_scratch_bytes(n), f32 ? flatten_scratch_bytes(nn_max, n) : (size_t)0);
+  PrepareArena arena;
+  CU(cudaMalloc((void**)&arena.base, fixed_bytes + work_bytes));
+  arena.cap = fixed_bytes + work_bytes;
+  struct ArenaFree {
+    rtc_ctx* c;
+    PrepareArena& a;
+    std::thread& t;
+    ~ArenaFree() {  // (after the helper thread has ended and everything queued on the two streams has run)
+      if (t.joinable()) t.join();
+      cudaStreamSynchronize(c->stream);
+      if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+      cudaFree(a.base);
+    }
+  };
+  std::thread uploader;
+  ArenaFree arena_free{ctx, arena, uploader};
+  auto carve = [&](size_t bytes) {
+    void* p = arena.base + arena.used;
+    arena.used += (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+    return p;
+  };
+  double* d_allboxes = (double*)carve(nz * 6 * sizeof(double));
+  double* d_boxes_c = (double*)carve(nz * 6 * sizeof(double));  // compacted (bounded only); unused when every primitive is bounded
+  int32_t* d_ids = (int32_t*)carve(nz * sizeof(int32_t));
+  int32_t* d_slot_prim = (int32_t*)carve(nz * sizeof(int32_t));
+  StagedPrim* d_staged = f32 ? (StagedPrim*)carve(nz * sizeof(StagedPrim)) : nullptr;
+
+  // ---- leaf boxes exactly as AABB.CreateFromBounded (AABB.cs:20-36): host threads -> pinned ring -> device ------------------
+  // primitives with infinite boxes (planes) stay out of the build and are chained above its root in ID order, like the host
+  // builder does; the bounded ones keep their order (ascending ID)
+  struct Unb {
+    int32_t id;
+    double box[6];
+  };
+  std::vector<Unb> unb;
+  std::mutex unb_mutex;
+  rc = staged_upload(ctx, ctx->stream, nz, 6 * sizeof(double), (char*)d_allboxes, [&](size_t i, char* dst) {
+    double* bx = (double*)dst;
+    rtcore::DescPrimitiveBounds(d, (int)i, bx, bx + 3);
+    bool finite = true;
+    for (int k = 0; k < 6; k++) finite = finite && std::isfinite(bx[k]);
+    if (!finite) {
+      Unb u;
+      u.id = (int32_t)i;
+      std::memcpy(u.box, bx, sizeof(u.box));
+      std::lock_guard<std::mutex> g(unb_mutex);
+      unb.push_back(u);
+    }
+  });
+  if (rc) return rc;
+  std::sort(unb.begin(), unb.end(), [](const Unb& x, const Unb& y) { return x.id < y.id; });
+  const int32_t nu = (int32_t)unb.size(), m = n - nu;
+  const double* d_boxes = d_allboxes;
+  const int32_t* d_prim_ids = nullptr;  // identity
+  std::vector<int32_t> ids;
+  if (nu > 0 && m > 0) {
+    ids.reserve(m);
+    size_t u = 0;
+    for (int32_t i = 0; i < n; i++) {
+      if (u < unb.size() && unb[u].id == i) {
+        u++;
+        continue;
+      }
+      ids.push_back(i);
+    }
+    CU(cudaMemcpyAsync(d_ids, ids.data(), (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = launch_gather_boxes(ctx->stream, m, d_ids, d_allboxes, d_boxes_c);
+    if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("gather boxes: ") + cudaGetErrorString(e));
+    CU(cudaStreamSynchronize(ctx->stream));  // (ids is read by the copy until here)
+    d_boxes = d_boxes_c;
+    d_prim_ids = d_ids;
+  }
+  st.boxes_ms = ms_since(t0);
+  const auto t1 = clk::now();
+
+  const int32_t nn = (m > 0 ? 2 * m - 1 : 0) + (m > 0 ? 2 * nu : (nu > 0 ? 2 * nu - 1 : 0));
+  rtc_bvh_node* d_bn = nullptr;
+  CU(cudaMalloc((void**)&d_bn, (size_t)nn * sizeof(rtc_bvh_node)));
+  ctx->d_bnodes = d_bn;  // (owned by the context from here; dropped again on failure)
+  ctx->n_bnodes = nn;
+  auto bail = [&](int code, const std::string& msg) {
+    if (uploader.joinable()) uploader.join();
+    cudaStreamSynchronize(ctx->stream);
+    drop_device_tree(ctx);
+    return fail(ctx, code, msg);
+  };
+
+  // the records travel on the copy stream, staged by a second host thread (float conversion and material packing on the host
+  // threads, through the same pinned ring) while this thread drives the level-synchronous build; the records kernel at the very
+  // end is the only reader
+  int up_rc = RTC_OK;
+  if (f32) {
+    uploader = std::thread([&]() {
+      cudaSetDevice(ctx->device);
+      up_rc = staged_upload(ctx, ctx->copy_stream, nz, sizeof(StagedPrim), (char*)d_staged, [&](size_t i, char* dst) {
+        StagedPrim* sp = (StagedPrim*)dst;
+        const double* g = &ctx->geom[i * RTC_GEOM_STRIDE];
+        for (int k = 0; k < 12; k++) sp->geom[k] = (float)g[k];
+        const double* mt = &ctx->material[i * RTC_MATERIAL_STRIDE];
+        DMat<float> dm;
+        pack_material(dm, mt, mt[13] > 0);  // Primitive.IsReflective (Primitive.cs:106)
+        std::memcpy(sp->mat, dm.w, sizeof(dm.w));
+        sp->kind_flags = (uint32_t)ctx->kind[i] | ((uint32_t)ctx->flags[i] << 8);
+        sp->xform = ctx->xform[i];
+        sp->pad[0] = sp->pad[1] = 0;
+      });
+      if (up_rc == RTC_OK && cudaEventRecord(ctx->ev_geom, ctx->copy_stream) != cudaSuccess) up_rc = RTC_ERR_CUDA;
+    });
+  }
+
+  // ---- the tree ----------------------------------------------------------------------------------------------------------
+  int32_t root = -1, levels = 0;
+  if (m > 0) {
+    if (builder == RTC_BUILDER_SAH) {
+      const size_t mark = arena.used;
+      cudaError_t e = build_bvh_sah_device(ctx->stream, &arena, ctx->h_pin, m, d_boxes, d_prim_ids, d_bn, &levels);
+      arena.used = mark;
+      if (e != cudaSuccess) return bail(RTC_ERR_CUDA, std::string("build_bvh_sah_device: ") + cudaGetErrorString(e));
+      root = 0;
+    } else {
+      std::vector<double> boxes((size_t)m * 6);
+      std::vector<int32_t> pid(m);
+      CU(cudaMemcpyAsync(boxes.data(), d_boxes, boxes.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      for (int32_t i = 0; i < m; i++) pid[i] = ids.empty() ? i : ids[i];
+      std::vector<rtc_bvh_node> hn((size_t)2 * m - 1);
+      cudaError_t e = build_bvh_ploc(ctx->stream, m, boxes.data(), pid.data(), radius, hn.data(), &root, &levels);
+      if (e != cudaSuccess) return bail(RTC_ERR_CUDA, std::string("build_bvh_ploc: ") + cudaGetErrorString(e));
+      CU(cudaMemcpyAsync(d_bn, hn.data(), hn.size() * sizeof(rtc_bvh_node), cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  if (nu > 0) {  // the chain of unbounded leaves above the root (bvh_builder.cpp: BuildBVH), first plane outermost-left
+    std::vector<rtc_bvh_node> chain;
+    rtc_bvh_node top;
+    std::memset(&top, 0, sizeof(top));
+    if (root >= 0) {
+      CU(cudaMemcpyAsync(&top, d_bn + root, sizeof(top), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+    int32_t next = m > 0 ? 2 * m - 1 : 0;
+    const int32_t chain_begin = next;
+    for (int32_t j = nu; j-- > 0;) {
+      rtc_bvh_node leaf;
+      std::memset(&leaf, 0, sizeof(leaf));
+      for (int k = 0; k < 3; k++) {
+        leaf.bmin[k] = unb[j].box[k];
+        leaf.bmax[k] = unb[j].box[3 + k];
+      }
+      leaf.left = leaf.right = -1;
+      leaf.prim = unb[j].id;
+      chain.push_back(leaf);
+      if (root < 0) {
+        root = next++;
+        top = leaf;
+        continue;
+      }
+      rtc_bvh_node par;
+      std::memset(&par, 0, sizeof(par));
+      par.left = next;
+      par.right = root;
+      par.prim = -1;
+      for (int k = 0; k < 3; k++) {
+        par.bmin[k] = std::fmin(leaf.bmin[k], top.bmin[k]);
+        par.bmax[k] = std::fmax(leaf.bmax[k], top.bmax[k]);
+      }
+      chain.push_back(par);
+      top = par;
+      root = next + 1;
+      next += 2;
+    }
+    CU(cudaMemcpyAsync(d_bn + chain_begin, chain.data(), chain.size() * sizeof(rtc_bvh_node), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->root = root;
+  st.build_levels = levels;
+  st.build_ms = ms_since(t1);
+  const auto t2 = clk::now();
+
+  if (!f32) {  // parity mode: the f64 layout is made on the host from the tree just built
+    rc = ensure_host_nodes(ctx);
+    if (rc) return bail(RTC_ERR_CUDA, "tree read-back failed");
+    cudaStreamSynchronize(ctx->stream);
+    free_dev_t(ctx->d_bnodes);  // (finish_bvh keeps the host tree)
+    ctx->n_bnodes = 0;
+    rc = finish_bvh(ctx);
+    st.flatten_ms = ms_since(t2);
+    st.total_ms = ms_since(t0);
+    st.n_bounded = m;
+    if (stats) *stats = st;
+    return rc;
+  }
+
+  // ---- the device layout ---------------------------------------------------------------------------------------------------
+  using S = rtc_baked;
+  if ((rc = ensure_seg(ctx, S::S_PRIMS, nz * sizeof(DPrim<float>))) || (rc = ensure_seg(ctx, S::S_MATS, nz * sizeof(DMat<float>))) ||
+      (rc = ensure_seg(ctx, S::S_AUX, nz * sizeof(int32_t))) || (rc = ensure_seg(ctx, S::S_PRIM_ID, nz * sizeof(int32_t))) ||
+      (rc = ensure_seg(ctx, S::S_ID_TO_SLOT, nz * sizeof(int32_t))) || (rc = ensure_seg(ctx, S::S_SGEOM, nz * sizeof(V4<float>))) ||
+      (rc = ensure_seg(ctx, S::S_NODES, 0)) || (rc = ensure_seg(ctx, S::S_UNBOUNDED, (size_t)nu * sizeof(uint32_t))) ||
+      (rc = ensure_seg(ctx, S::S_XFORMS, (size_t)std::max(1, ctx->n_xforms) * sizeof(DXform<float>))))
+    return bail(rc, ctx->err);
+  FlattenInput fin;
+  fin.nodes = d_bn;
+  fin.n_nodes = nn;
+  fin.root = root;
+  fin.n_prims = n;
+  fin.staged = d_staged;
+  fin.records_ready = nullptr;  // (joined below: the event is recorded by the helper thread)
+  fin.alloc_ctx = ctx;
+  fin.alloc_qnodes = [](void* c, size_t bytes, void** out) {
+    rtc_ctx* cx = (rtc_ctx*)c;
+    const int r = ensure_seg(cx, rtc_baked::S_QNODES, bytes);
+    *out = cx->d_qnodes;
+    return r;
+  };
+  FlattenOutput fout;
+  fout.slot_prim = d_slot_prim;
+  fout.prims = ctx->d_prims;
+  fout.mats = ctx->d_mats;
+  fout.sgeom = ctx->d_sgeom;
+  fout.aux = ctx->d_aux;
+  fout.prim_id = ctx->d_prim_id;
+  fout.id_to_slot = ctx->d_id_to_slot;
+  // the helper thread has usually finished long before the tree has; its event orders the records kernel behind the copies
+  if (uploader.joinable()) uploader.join();
+  if (up_rc != RTC_OK) return bail(up_rc, "staging the scene records failed");
+  fin.records_ready = ctx->ev_geom;
+  std::string ferr;
+  rc = flatten_device(ctx->stream, &arena, ctx->h_pin, fin, fout, ferr);
+  if (rc) return bail(rc, ferr);
+  if (fout.depth + 1 > kQStackMax)
+    return bail(RTC_ERR_UNSUPPORTED, "8-wide BVH depth " + std::to_string(fout.depth) + " exceeds the traversal stack (" + std::to_string(kQStackMax - 1) + ")");
+  if (fout.n_qnodes == 0 && ctx->d_qnodes) {  // no bounded primitive: the kernel keys on a null qnodes pointer
+    cudaFree(ctx->d_qnodes);
+    ctx->d_qnodes = nullptr;
+    ctx->seg_cap[S::S_QNODES] = 0;
+  }
+  // unbounded leaf references and the transform rows: small, made on the host like build_device_scene does
+  std::vector<uint32_t> unb_refs;
+  for (size_t r = 0; r < fout.unbounded_prims.size(); r++) {
+    const int32_t p = fout.unbounded_prims[r];
+    unb_refs.push_back(prep::leaf_ref_of(ctx->kind[p], ctx->flags[p], ctx->xform[p], (uint32_t)(fout.n_bounded + (int32_t)r)));
+  }
+  if (!unb_refs.empty())
+    CU(cudaMemcpyAsync(ctx->d_unbounded, unb_refs.data(), unb_refs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<DXform<float>> dx(std::max(1, ctx->n_xforms));
+  std::memset(dx.data(), 0, dx.size() * sizeof(DXform<float>));
+  for (int32_t j = 0; j < ctx->n_xforms; j++) {
+    const double* x = &ctx->xforms[(size_t)j * RTC_XFORM_STRIDE];
+    for (int mtx = 0; mtx < 3; mtx++)
+      for (int row = 0; row < 3; row++) {
+        const double* r = x + mtx * 16 + row * 4;
+        dx[j].r[mtx * 3 + row] = V4<float>{(float)r[0], (float)r[1], (float)r[2], (float)r[3]};
+      }
+  }
+  if (ctx->n_xforms > 0)
+    for (int32_t p = 0; p < n; p++)  // vertex-normal triangles keep n0,n1,n2 in the first 9 doubles of their row
+      if (ctx->kind[p] == RTC_KIND_TRIANGLE && (ctx->flags[p] & RTC_FLAG_VNORMALS) && ctx->xform[p] >= 0) {
+        const int32_t j = ctx->xform[p];
+        const double* x = &ctx->xforms[(size_t)j * RTC_XFORM_STRIDE];
+        for (int k2 = 0; k2 < 3; k2++) dx[j].r[k2] = V4<float>{(float)x[k2 * 3], (float)x[k2 * 3 + 1], (float)x[k2 * 3 + 2], 0.0f};
+      }
+  CU(cudaMemcpyAsync(ctx->d_xforms, dx.data(), dx.size() * sizeof(DXform<float>), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->n_unbounded = nu;
+  ctx->root_node = 0;
+  ctx->bvh_depth = fout.depth;
+  const size_t sb[S::S_COUNT] = {0, (size_t)fout.n_qnodes * sizeof(CNode), (size_t)nu * sizeof(uint32_t), nz * sizeof(DPrim<float>),
+                                 nz * sizeof(DMat<float>), dx.size() * sizeof(DXform<float>), nz * sizeof(int32_t), nz * sizeof(int32_t),
+                                 nz * sizeof(int32_t), nz * sizeof(V4<float>)};
+  for (int i = 0; i < S::S_COUNT; i++) ctx->seg_bytes[i] = sb[i];
+  delete ctx->baked;
+  ctx->baked = nullptr;
+  ctx->bvh_set = true;
+  st.flatten_ms = ms_since(t2);
+  st.total_ms = ms_since(t0);
+  st.wide_depth = fout.depth;
+  st.n_wide_nodes = fout.n_qnodes;
+  st.n_bounded = fout.n_bounded;
+  if (stats) *stats = st;
+  if (std::getenv("RTC_B200_VERBOSE"))
+    std::fprintf(stderr, "[rtcore_b200] prepare on the device: %d primitives, boxes %.1f ms, build %.1f ms (%d levels), flatten %.1f ms, total %.1f ms; "
+                         "%d wide nodes, depth %d\n", n, st.boxes_ms, st.build_ms, levels, st.flatten_ms, st.total_ms, fout.n_qnodes, fout.depth);
+  return RTC_OK;
+}
+
 int rtc_bake(rtc_ctx* ctx, rtc_baked** out) {
   if (!ctx || !out) return RTC_ERR_INVALID;
   *out = nullptr;
-  if (!ctx->bvh_set || !ctx->baked) return fail(ctx, RTC_ERR_STATE, "no scene + BVH to bake (rtc_upload_scene, then rtc_upload_bvh or rtc_build_bvh)");
+  if (!ctx->bvh_set) return fail(ctx, RTC_ERR_STATE, "no scene + BVH to bake (rtc_upload_scene, then rtc_upload_bvh, rtc_build_bvh or rtc_prepare_device)");
   cudaSetDevice(ctx->device);
+  if (!ctx->baked) {  // prepared on the device, or received from another rank: the image is read back segment by segment
+    int rc = wait_shading_upload(ctx);
+    if (rc) return rc;
+    rtc_baked* c = new rtc_baked();
+    c->precision = ctx->precision;
+    c->n_prims = ctx->n_prims;
+    c->n_unbounded = ctx->n_unbounded;
+    c->n_xforms = ctx->n_xforms;
+    c->bvh_depth = ctx->bvh_depth;
+    c->root_node = ctx->root_node;
+    size_t total = 0;
+    for (int i = 0; i < rtc_baked::S_COUNT; i++) {
+      c->off[i] = total;
+      c->bytes[i] = ctx->seg_bytes[i];
+      total += (ctx->seg_bytes[i] + 255) & ~(size_t)255;
+    }
+    if (!c->alloc(total)) {
+      delete c;
+      return fail(ctx, RTC_ERR_NOMEM, "host allocation for the baked scene failed");
+    }
+    const void* src[rtc_baked::S_COUNT] = {ctx->d_nodes, ctx->d_qnodes, ctx->d_unbounded, ctx->d_prims, ctx->d_mats,
+                                           ctx->d_xforms, ctx->d_aux, ctx->d_prim_id, ctx->d_id_to_slot, ctx->d_sgeom};
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < rtc_baked::S_COUNT && e == cudaSuccess; i++)
+      if (c->bytes[i]) e = cudaMemcpyAsync(c->host + c->off[i], src[i], c->bytes[i], cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      delete c;
+      return fail(ctx, RTC_ERR_CUDA, std::string("rtc_bake (read-back): ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return RTC_OK;
+  }
   rtc_baked* c = new rtc_baked();
   const rtc_baked* b = ctx->baked;
   c->precision = b->precision;
@@ -1610,6 +2086,7 @@ int rtc_upload_baked(rtc_ctx* ctx, const rtc_baked* baked) {
     ctx->xforms.clear();
     ctx->nodes.clear();
     ctx->root = -1;
+    drop_device_tree(ctx);
   }
   ctx->scene_set = true;
   ctx->bvh_set = true;
@@ -1623,10 +2100,19 @@ int64_t rtc_baked_bytes(const rtc_baked* baked) {
   return t;
 }
 
+int rtc_baked_segment(const rtc_baked* baked, int32_t segment, const void** data, int64_t* bytes) {
+  static_assert((int)rtc_baked::S_COUNT == (int)RTC_BAKED_SEGMENTS, "segment count in the public header");
+  if (!baked || !data || !bytes || segment < 0 || segment >= rtc_baked::S_COUNT) return RTC_ERR_INVALID;
+  *data = baked->host + baked->off[segment];
+  *bytes = (int64_t)baked->bytes[segment];
+  return RTC_OK;
+}
+
 void rtc_baked_free(rtc_baked* baked) { delete baked; }
 
 int rtc_get_bvh_size(rtc_ctx* ctx, int32_t* n_nodes, int32_t* root) {
   if (!ctx || !n_nodes || !root) return RTC_ERR_INVALID;
+  if (ctx->bvh_set && ensure_host_nodes(ctx)) return RTC_ERR_CUDA;
   if (!ctx->bvh_set || ctx->nodes.empty()) return fail(ctx, RTC_ERR_STATE, "no host-side BVH (none set, or the scene came from rtc_upload_baked)");
   *n_nodes = (int32_t)ctx->nodes.size();
   *root = ctx->root;
@@ -1636,6 +2122,7 @@ int rtc_get_bvh_size(rtc_ctx* ctx, int32_t* n_nodes, int32_t* root) {
 int rtc_get_bvh(rtc_ctx* ctx, int32_t capacity, rtc_bvh_node* nodes) {
   if (!ctx || !nodes) return RTC_ERR_INVALID;
   if (!ctx->bvh_set) return fail(ctx, RTC_ERR_STATE, "no BVH");
+  if (ensure_host_nodes(ctx)) return RTC_ERR_CUDA;
   if (capacity < (int32_t)ctx->nodes.size()) return fail(ctx, RTC_ERR_INVALID, "capacity too small");
   std::memcpy(nodes, ctx->nodes.data(), ctx->nodes.size() * sizeof(rtc_bvh_node));
   return RTC_OK;
@@ -1814,7 +2301,12 @@ int rtc_tonemap_argb(rtc_ctx* ctx, double exposure, const double back_rgb[3], do
   if (ctx->argb_cap < n) {  // persistent image buffers, sized once per image size
     if (ctx->ui_stream) CU(cudaStreamSynchronize(ctx->ui_stream));
     free_dev_t(ctx->d_argb);
-    if (ctx->h_argb) cudaFreeHost(ctx->h_argb);
+    for (int i = 0; i < 2; i++) {
+    if (ctx->h_ring[i]) cudaFreeHost(ctx->h_ring[i]);
+    if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
+  }
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->h_argb) cudaFreeHost(ctx->h_argb);
     ctx->h_argb = nullptr;
     ctx->argb_cap = 0;
     CU(cudaMalloc((void**)&ctx->d_argb, sizeof(uint32_t) * n));
@@ -1962,6 +2454,7 @@ int rtc_debug_raycast(rtc_ctx* ctx, int32_t mode, int32_t* out) {
   if (rc) return rc;
   const int w = ctx->par.width, h = ctx->par.height;
   const size_t n = (size_t)w * h;
+  if (mode == RTC_OVERLAY_BOUNDING_VOLUMES && ensure_host_nodes(ctx)) return RTC_ERR_CUDA;
   if (mode == RTC_OVERLAY_BOUNDING_VOLUMES && ctx->nodes.empty())
     return fail(ctx, RTC_ERR_STATE, "no host-side BVH (the scene came from rtc_upload_baked)");
   // persistent scratch: [w*h ids | the reference-shaped tree for the box-count mode]
@@ -2219,6 +2712,7 @@ int rtc_bcast_scene(rtc_ctx* ctx, int32_t root) {
     ctx->xforms.clear();
     ctx->nodes.clear();
     ctx->root = -1;
+    drop_device_tree(ctx);
     delete ctx->baked;
     ctx->baked = nullptr;
     ctx->scene_set = true;

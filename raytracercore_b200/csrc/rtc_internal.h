@@ -22,6 +22,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+#include <vector>
+
 #include "../../include/rtcore_b200.h"
 
 namespace rtc {
@@ -243,6 +246,54 @@ cudaError_t launch_overlay_boxcount(cudaStream_t s, const rtc_bvh_node* nodes, i
 // (lo[3], hi[3]) f64 on the host, prim_ids: their primitive IDs; nodes_out: 2m-1 nodes (host), leaves first.
 cudaError_t build_bvh_ploc(cudaStream_t stream, int32_t m, const double* boxes, const int32_t* prim_ids, int radius,
                            rtc_bvh_node* nodes_out, int32_t* root_out, int32_t* rounds_out);
+
+// Scene.Prepare on the device (prepare_device.cu).
+// One device allocation per call, carved up by the two passes below (base / cap set by the caller, used = bytes handed out).
+struct PrepareArena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+};
+// One primitive as the host stages it for the device flatten, in input (primitive ID) order: the geometry as floats, the
+// material record already packed (pack_material), kind | flags << 8 and the transform row.
+struct alignas(16) StagedPrim {
+  float geom[12];
+  uint32_t mat[8];
+  uint32_t kind_flags;
+  int32_t xform;
+  uint32_t pad[2];
+};
+static_assert(sizeof(StagedPrim) == 96, "StagedPrim layout");
+// The host builder's binned-SAH tree (host/bvh_builder.cpp), node for node, over m bounded primitives: d_boxes m x (lo[3],
+// hi[3]) f64 leaf boxes, d_prim_ids their primitive IDs (ascending; null = identity), d_nodes room for 2m-1 nodes (root =
+// node 0). h_pin: 8 x int32 of pinned host memory. Synchronises `stream`.
+size_t build_bvh_sah_scratch_bytes(int32_t m);
+cudaError_t build_bvh_sah_device(cudaStream_t stream, PrepareArena* arena, int32_t* h_pin, int32_t m, const double* d_boxes,
+                                 const int32_t* d_prim_ids, rtc_bvh_node* d_nodes, int32_t* levels_out);
+// The f32-mode flattening of rtc_api.cu (build_device_scene) on the device, byte-identical output. All pointers are device
+// pointers.
+struct FlattenInput {
+  const rtc_bvh_node* nodes;
+  int32_t n_nodes, root, n_prims;
+  const StagedPrim* staged;
+  cudaEvent_t records_ready;  // optional: `staged` is complete once this event has passed (it is read last)
+  // called once the number of wide nodes is known: a device buffer of `bytes` for them (the context's scene segment)
+  int (*alloc_qnodes)(void* alloc_ctx, size_t bytes, void** out);
+  void* alloc_ctx;
+};
+struct FlattenOutput {
+  CNode* qnodes = nullptr;    // from alloc_qnodes; null if there is no bounded primitive
+  int32_t n_qnodes = 0, depth = 0, n_bounded = 0;
+  std::vector<int32_t> unbounded_prims;  // primitive IDs of the unbounded leaves in left-first order (slots n_bounded ...)
+  // caller-allocated, n_prims entries each
+  int32_t* slot_prim = nullptr;
+  void *prims = nullptr, *mats = nullptr, *sgeom = nullptr;
+  int32_t *aux = nullptr, *prim_id = nullptr, *id_to_slot = nullptr;
+};
+// out[i] = all[ids[i]] for 6-double boxes (the bounded primitives' boxes, compacted)
+cudaError_t launch_gather_boxes(cudaStream_t stream, int32_t m, const int32_t* d_ids, const double* d_all, double* d_out);
+size_t flatten_scratch_bytes(int32_t n_nodes, int32_t n_prims);
+int flatten_device(cudaStream_t stream, PrepareArena* arena, int32_t* h_pin, const FlattenInput& in, FlattenOutput& out,
+                   std::string& err);  // RTC_OK or an RTC_ERR_* code
 
 // mode-independent
 // planes -= base (rtc_reduce_accum after an all-reduce: only the samples rendered since then are contributed again)

@@ -149,9 +149,10 @@ void PrimitiveBounds(const Primitive& p, double bmin[3], double bmax[3]) {  // A
   bmax[0] = hi.X; bmax[1] = hi.Y; bmax[2] = hi.Z;
 }
 
-static Primitive PrimitiveFromDesc(const rtc_scene_desc& d, int i) {
+// (fills the fields the bounds read, into a caller-provided object: a Primitive with its three matrices is ~900 bytes, and the
+// bounds of a million flattened triangles are computed one after the other)
+static void PrimitiveFromDesc(const rtc_scene_desc& d, int i, Primitive& p) {
   const double* g = d.geom + (size_t)i * RTC_GEOM_STRIDE;
-  Primitive p;
   p.Kind = d.kind[i];
   uint8_t f = d.flags[i];
   if (p.Kind == RTC_KIND_TRIANGLE) {
@@ -176,11 +177,11 @@ static Primitive PrimitiveFromDesc(const rtc_scene_desc& d, int i) {
     p.PlaneNormal = Vec4D(g[0], g[1], g[2], 0);
     p.OriginDistance = g[3];
   }
-  return p;
 }
 
 void DescPrimitiveBounds(const rtc_scene_desc& d, int i, double bmin[3], double bmax[3]) {
-  Primitive p = PrimitiveFromDesc(d, i);
+  static thread_local Primitive p;
+  PrimitiveFromDesc(d, i, p);
   PrimitiveBounds(p, bmin, bmax);
   if (p.Kind == RTC_KIND_TRIANGLE) {
     for (int k = 0; k < 3; k++) {

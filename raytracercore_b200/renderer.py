@@ -24,6 +24,17 @@ class Baked:
     def nbytes(self):
         return int(N.lib.rtc_baked_bytes(self._h))
 
+    def segments(self):
+        """{name: bytes} of the image's arrays (copies)."""
+        out = {}
+        for i, name in enumerate(N.BAKED_SEGMENT_NAMES):
+            p, nb = C.c_void_p(), C.c_int64()
+            rc = N.lib.rtc_baked_segment(self._h, i, C.byref(p), C.byref(nb))
+            if rc != N.RTC_OK:
+                raise N.RtcError(rc, "rtc_baked_segment")
+            out[name] = C.string_at(p, nb.value) if nb.value else b""
+        return out
+
     def close(self):
         if self._h:
             N.lib.rtc_baked_free(self._h)
@@ -88,6 +99,12 @@ class Context:
         self._ck(N.lib.rtc_build_bvh_device(self._h, radius, C.byref(rounds)))
         return rounds.value
 
+    def prepare_device(self, builder=N.RTC_BUILDER_SAH, radius=0):
+        """Scene.Prepare wholly on the GPU (tree + device layout); returns the rtc_prepare_stats."""
+        st = N.PrepareStats()
+        self._ck(N.lib.rtc_prepare_device(self._h, builder, radius, C.byref(st)))
+        return st
+
     def get_bvh(self):
         n = C.c_int32()
         root = C.c_int32()
@@ -112,11 +129,15 @@ class Context:
         self._ck(N.lib.rtc_set_params(self._h, C.byref(par)))
         self.width, self.height = par.width, par.height
 
-    def load(self, scene, seed=1, camera=None, use_scene_bvh=True, device_bvh=False, radius=0):
+    def load(self, scene, seed=1, camera=None, use_scene_bvh=True, device_bvh=False, radius=0, device_prepare=None):
         """Scene.Prepare + FullRaytracer.Start's set-up (FullRaytracer.cs:253-269) in one call. device_bvh: build the
-        tree on the GPU (rtc_build_bvh_device) instead of taking the host scene's accelerator."""
+        tree on the GPU (rtc_build_bvh_device) instead of taking the host scene's accelerator. device_prepare: a builder
+        (RTC_BUILDER_SAH / RTC_BUILDER_PLOC): tree and device layout both made on the GPU (rtc_prepare_device)."""
         self.upload_scene(scene)
-        if device_bvh:
+        self.prepare_stats = None
+        if device_prepare is not None:
+            self.prepare_stats = self.prepare_device(device_prepare, radius)
+        elif device_bvh:
             self.build_bvh(device=True, radius=radius)
         elif use_scene_bvh:
             nodes, n, root = scene.bvh()

@@ -121,7 +121,8 @@ def cs_structs():
 C_SIZES = {"int32_t": 4, "uint32_t": 4, "int64_t": 8, "uint64_t": 8, "double": 8, "uint8_t": 1, "ptr": 8, "rtc_hit": None}
 PAIRS = {"rtc_scene_desc": ("RtcSceneDesc", N.SceneDesc), "rtc_bvh_node": ("RtcBvhNode", N.BvhNode), "rtc_camera": ("RtcCamera", N.Camera),
          "rtc_params": ("RtcParams", N.Params), "rtc_ray": ("RtcRay", N.Ray), "rtc_hit": ("RtcHit", N.Hit),
-         "rtc_debug_ray": ("RtcDebugRay", N.DebugRay), "rtc_stats": ("RtcStats", N.Stats)}
+         "rtc_debug_ray": ("RtcDebugRay", N.DebugRay), "rtc_stats": ("RtcStats", N.Stats),
+         "rtc_prepare_stats": ("RtcPrepareStats", N.PrepareStats)}
 
 
 def test_struct_layouts_match_the_header_and_the_ctypes_view():
