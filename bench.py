@@ -243,14 +243,32 @@ class Job:
         self.sc = None
         t = time.time()
         meta = [None]
+        self.prepare = None
         if rank == 0:
+            from raytracercore_b200 import RTC_BUILDER_SAH
             self.sc = make_scene(workload)
-            self.sc.bvh()  # Scene.Prepare: host BVH build (cached between renders, like the reference)
-            self.t_bvh = time.time() - t
-            t = time.time()
-            self.ctx.load(self.sc, seed=1)
-            self.ctx.sync()
-            self.t_flatten = time.time() - t
+            self.sc.desc()  # (the flattened description, made once by the host scene: not part of Scene.Prepare)
+            if os.environ.get("RTC_BENCH_HOST_PREPARE") == "1":  # the round-1 path: host binned SAH, host flatten, H2D of the image
+                t = time.time()
+                self.sc.bvh()
+                self.t_bvh = time.time() - t
+                t = time.time()
+                self.ctx.load(self.sc, seed=1)
+                self.ctx.sync()
+                self.t_flatten = time.time() - t
+                self.prepare = {"where": "host", "total_s": self.t_bvh + self.t_flatten}
+            else:
+                # Scene.Prepare on the device (rtc_prepare_device): the host SAH tree, node for node, and the device layout, byte for
+                # byte, without the tree or the image ever crossing PCIe (tests/test_gpu_prepare.py)
+                t = time.time()
+                self.ctx.load(self.sc, seed=1, device_prepare=RTC_BUILDER_SAH)
+                self.ctx.sync()
+                total = time.time() - t
+                st = self.ctx.prepare_stats
+                self.t_bvh = (st.boxes_ms + st.build_ms) * 1e-3
+                self.t_flatten = total - self.t_bvh  # rtc_upload_scene's copy of the description + collapse / quantisation / records
+                self.prepare = {"where": "device", "total_s": total, "boxes_ms": st.boxes_ms, "build_ms": st.build_ms, "flatten_ms": st.flatten_ms,
+                                "build_levels": st.build_levels, "wide_nodes": st.n_wide_nodes, "wide_depth": st.wide_depth}
             self.par, self.cam = self.sc.params(1), self.sc.camera()
             meta = [dict(par=bytes(self.par), cam=bytes(self.cam), n_prims=self.sc.n_prims, t_bvh=self.t_bvh, t_flatten=self.t_flatten)]
         self.t_bcast = 0.0
@@ -528,7 +546,8 @@ def main():
             "dtype": args.precision, "data": "synthetic",
             "config": static_config(args.workload, spp, world, job.n_prims),
             "measured": {"spp_mpix_per_s": res["paths"] / (res["ms"] * 1e-3) / 1e6, "rays_per_path": res["rays"] / max(1.0, res["paths"]),
-                         "bvh_build_s": job.t_bvh, "flatten_upload_s": job.t_flatten, "scene_bcast_s": job.t_bcast},
+                         "bvh_build_s": job.t_bvh, "flatten_upload_s": job.t_flatten, "scene_bcast_s": job.t_bcast,
+                         "prepare": job.prepare},
             "roofline": roofline,
             "gpu_launches": int(sum(st.launches[k] for k in range(N.RTC_K_COUNT))),
             "clocks": res["clocks"],
@@ -563,7 +582,7 @@ def main():
                     d["e2e"] = e
                 return d
             c5 = {"config": static_config("soup10m", w5["spp"], world, j5.n_prims), "n_gpus": world,
-                  "bvh_build_s": j5.t_bvh, "flatten_upload_s": j5.t_flatten, "scene_bcast_s": j5.t_bcast,
+                  "bvh_build_s": j5.t_bvh, "flatten_upload_s": j5.t_flatten, "scene_bcast_s": j5.t_bcast, "prepare": j5.prepare,
                   "weak": pack(weak, weak_e2e, w5["spp"], "weak")}
             if strong:
                 c5["strong"] = pack(strong, strong_e2e, C5_STRONG_TOTAL_SPP // world, "strong")

