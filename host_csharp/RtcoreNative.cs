@@ -114,6 +114,7 @@ namespace RaytracerCore.Raytracing.Gpu
 		[DllImport(Lib)] public static extern int rtc_trace_closest(IntPtr ctx, long n, RtcRay* rays, RtcHit* skip, RtcHit* hits);
 		[DllImport(Lib)] public static extern int rtc_camera_rays(IntPtr ctx, long n, int* xy, uint* sample, RtcRay* rays);
 		[DllImport(Lib)] public static extern int rtc_build_bvh_device(IntPtr ctx, int radius, out int rounds);
+		[DllImport(Lib)] public static extern int rtc_debug_create_horizon(IntPtr ctx, long n, double* poleZTheta, double* xyz);
 		[DllImport(Lib)] public static extern int rtc_render(IntPtr ctx, int x0, int y0, int x1, int y1, uint firstSample, uint nSamples);
 		[DllImport(Lib)] public static extern int rtc_render_read(IntPtr ctx, uint firstSample, uint nSamples, double* rgbSum, uint* samples, uint* misses);
 		[DllImport(Lib)] public static extern int rtc_sync(IntPtr ctx);

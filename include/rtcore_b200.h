@@ -243,6 +243,10 @@ int rtc_set_params(rtc_ctx* ctx, const rtc_params* params);
 int rtc_trace_closest(rtc_ctx* ctx, int64_t n, const rtc_ray* rays, const rtc_hit* skip, rtc_hit* out);
 /* Raytracer.GetCameraRay (Raytracer.cs:262-282) for n (x, y, sample) triples; xy is n*2 int32. */
 int rtc_camera_rays(rtc_ctx* ctx, int64_t n, const int32_t* xy, const uint32_t* sample, rtc_ray* out);
+/* Vec4D.CreateHorizon(pole, z, theta) (Vec4D.cs:33-58: the lobe sample of RandomShine / the diffuse bounce, Raytracer.cs:51-61)
+ * as the shading kernel of this context's arithmetic mode evaluates it: n tuples (pole.xyz, z, theta) in, n x xyz out. A
+ * known-answer hook for the parity tests, like rtc_camera_rays. */
+int rtc_debug_create_horizon(rtc_ctx* ctx, int64_t n, const double* pole_z_theta, double* out);
 /* n_samples passes of Raytracer.Render over the pixel rectangle [x0,x1) x [y0,y1) (Raytracer.cs:302-327),
  * samples first_sample .. first_sample+n_samples-1 of every pixel, accumulated like FullRaytracer.cs:326-339.
  * Asynchronous on the context's stream; rtc_sync / rtc_read_accum / rtc_tonemap_argb wait for it. */

@@ -112,6 +112,7 @@ SIGNATURES = {
     "rtc_trace_closest": (C.c_int, [_P, C.c_int64, _P, _P, _P]),
     "rtc_camera_rays": (C.c_int, [_P, C.c_int64, _P, _P, _P]),
     "rtc_build_bvh_device": (C.c_int, [_P, C.c_int32, _P]),
+    "rtc_debug_create_horizon": (C.c_int, [_P, C.c_int64, _P, _P]),
     "rtc_render": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32]),
     "rtc_sync": (C.c_int, [_P]),
     "rtc_clear_accum": (C.c_int, [_P]),

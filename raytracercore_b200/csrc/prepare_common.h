@@ -68,6 +68,9 @@ RTC_HD int32_t resolve(const rtc_bvh_node* nodes, const int32_t* nf, int32_t i) 
 // inner node either becomes a wide node itself (its area + its two sides spread over 8 slots) or hands its slots on to its
 // two sides. Evaluated children-first; cut[j] is the left side's share when j slots are split. Tl / Tr: the tables of the
 // (resolved) left and right child, index 0 unused.
+#ifndef RTC_COLLAPSE_WIDTH
+#define RTC_COLLAPSE_WIDTH 8  // children per wide node the collapse aims for (tuning experiments: narrower trees in the 8-slot node)
+#endif
 RTC_HD void dp_node(const float* Tl, const float* Tr, double area, float* Ti, uint8_t* cut_i) {
   float D[9];
   for (int j = 2; j <= 8; j++) {
@@ -84,7 +87,7 @@ RTC_HD void dp_node(const float* Tl, const float* Tr, double area, float* Ti, ui
     D[j] = bestv;
     cut_i[j] = (uint8_t)bestk;
   }
-  const float as_node = (float)area + D[8];
+  const float as_node = (float)area + D[RTC_COLLAPSE_WIDTH];
   Ti[1] = as_node;
   for (int j = 2; j <= 7; j++) Ti[j] = as_node < D[j] ? as_node : D[j];
 }
@@ -98,7 +101,7 @@ RTC_HD int gather_children(const TreeView& t, int32_t m, int32_t* kids) {
   It st[32];
   int sp = 0, nk = 0;
   st[sp].node = m;
-  st[sp].slots = 8;
+  st[sp].slots = RTC_COLLAPSE_WIDTH;
   st[sp].force_split = 1;
   sp++;
   while (sp > 0) {

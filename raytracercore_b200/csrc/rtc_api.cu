@@ -2195,6 +2195,24 @@ int rtc_camera_rays(rtc_ctx* ctx, int64_t n, const int32_t* xy, const uint32_t* 
   return RTC_OK;
 }
 
+int rtc_debug_create_horizon(rtc_ctx* ctx, int64_t n, const double* pole_z_theta, double* out) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!pole_z_theta || !out))) return fail(ctx, RTC_ERR_INVALID, "pole_z_theta/out must not be null");
+  if (n == 0) return RTC_OK;
+  cudaSetDevice(ctx->device);
+  int rc = ensure_scratch(ctx, (size_t)n * 8 * sizeof(double));
+  if (rc) return rc;
+  double* din = (double*)ctx->d_scratch;
+  double* dout = din + 5 * n;
+  CU(cudaMemcpyAsync(din, pole_z_theta, sizeof(double) * 5 * n, cudaMemcpyHostToDevice, ctx->stream));
+  LaunchCfg cfg{ctx->stream, ctx->sm_count, false};
+  cudaError_t e = ctx->precision == RTC_F64 ? Kernels<double>::horizon(cfg, n, din, dout) : Kernels<float>::horizon(cfg, n, din, dout);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("create_horizon: ") + cudaGetErrorString(e));
+  return RTC_OK;
+}
+
 int rtc_render(rtc_ctx* ctx, int32_t x0, int32_t y0, int32_t x1, int32_t y1, uint32_t first_sample, uint32_t n_samples) {
   if (!ctx) return RTC_ERR_INVALID;
   int rc = ready(ctx, true);

@@ -1937,6 +1937,27 @@ cudaError_t Kernels<R>::camera_rays(const LaunchCfg& cfg, const CameraView<R>& c
   return cudaGetLastError();
 }
 
+// Vec4D.CreateHorizon (Vec4D.cs:33-58) for n (pole, z, theta) tuples, as k_shade evaluates it in this arithmetic mode
+__device__ __forceinline__ V3<double> horizon_of(const V3<double>& pole, double z, double theta) { return create_horizon<double>(pole, z, theta); }
+__device__ __forceinline__ V3<float> horizon_of(const V3<float>& pole, float z, float theta) {
+  return create_horizon_f32(pole, z, xsqrt(1.0f - z * z), theta * 0.15915494309189535f);
+}
+template <typename R>
+__global__ void k_horizon(int64_t n, const double* in, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const V3<R> v = horizon_of(mk3((R)in[5 * i], (R)in[5 * i + 1], (R)in[5 * i + 2]), (R)in[5 * i + 3], (R)in[5 * i + 4]);
+  out[3 * i] = v.x;
+  out[3 * i + 1] = v.y;
+  out[3 * i + 2] = v.z;
+}
+template <typename R>
+cudaError_t Kernels<R>::horizon(const LaunchCfg& cfg, int64_t n, const double* in, double* out) {
+  if (n == 0) return cudaSuccess;
+  k_horizon<R><<<div_up(n, kStreamThreads), kStreamThreads, 0, cfg.stream>>>(n, in, out);
+  return cudaGetLastError();
+}
+
 template <typename R>
 cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, bool identity_queue) {
   const size_t smem = Num<R>::is_f64 ? (size_t)sc.q_stack * kTraceThreads * (4 + sizeof(R))

@@ -216,6 +216,8 @@ struct Kernels {
   // explicit (x,y,sample) list -> rtc_ray (f64) ; used by rtc_camera_rays
   static cudaError_t camera_rays(const LaunchCfg& cfg, const CameraView<R>& cam, const ParamsView<R>& par, int64_t n,
                                  const int32_t* xy, const uint32_t* sample, rtc_ray* out);
+  // CreateHorizon for n (pole.xyz, z, theta) tuples (rtc_debug_create_horizon)
+  static cudaError_t horizon(const LaunchCfg& cfg, int64_t n, const double* in, double* out);
   // bounce `bounce`: reads queue[q] (nullptr semantics: identity when bounce == 0) and the paths' hpos / dir, writes thit
   static cudaError_t trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, bool identity_queue);
   static cudaError_t shade(const LaunchCfg& cfg, const SceneView<R>& sc, const ParamsView<R>& par, const Band& band,

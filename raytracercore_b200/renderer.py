@@ -99,6 +99,13 @@ class Context:
         self._ck(N.lib.rtc_build_bvh_device(self._h, radius, C.byref(rounds)))
         return rounds.value
 
+    def create_horizon(self, pole_z_theta):
+        """Vec4D.CreateHorizon on the device for an (n, 5) array of (pole.xyz, z, theta); returns (n, 3)."""
+        a = np.ascontiguousarray(pole_z_theta, dtype=np.float64).reshape(-1, 5)
+        out = np.zeros((len(a), 3), np.float64)
+        self._ck(N.lib.rtc_debug_create_horizon(self._h, len(a), _ptr(a), _ptr(out)))
+        return out
+
     def prepare_device(self, builder=N.RTC_BUILDER_SAH, radius=0):
         """Scene.Prepare wholly on the GPU (tree + device layout); returns the rtc_prepare_stats."""
         st = N.PrepareStats()

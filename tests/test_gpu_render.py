@@ -495,3 +495,28 @@ def test_two_wavefronts_in_flight_render_the_same_planes():
         assert all(np.array_equal(x, y) for x, y in zip(out[1][k], out[2][k]))
     assert out[1][2:] == out[2][2:]
     assert np.all(out[2][1][1] + out[2][1][2] == 18)
+
+
+@pytest.mark.gpu
+def test_create_horizon_on_the_device_against_the_oracle():
+    """Vec4D.CreateHorizon (Vec4D.cs:33-58), evaluated directly: the lobe sample around a pole at polar
+    cosine z and azimuth theta. f64: the oracle's value to rounding; f32: to 1e-5 (approximate sine / cosine / reciprocal
+    square root). Includes the pole along the z axis (the (1, 0, 0) fall-back of the cross product) and z = 1."""
+    import math
+    rng = np.random.default_rng(11)
+    n = 4096
+    pole = rng.normal(size=(n, 3))
+    pole /= np.linalg.norm(pole, axis=1, keepdims=True)
+    pole[:4] = [[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0]]
+    z = rng.uniform(0, 1, n)
+    z[4:8] = [0.0, 1.0, 0.5, 0.999999]
+    theta = rng.uniform(0, 2 * math.pi, n)
+    theta[:2] = [0.0, math.pi / 2]
+    tuples = np.concatenate([pole, z[:, None], theta[:, None]], axis=1)
+    want = np.array([O.create_horizon(pole[i], z[i], theta[i]) for i in range(n)])
+    for prec, tol in ((RTC_F64, 1e-12), (RTC_F32, 1e-5)):
+        ctx = Context(0, prec)
+        got = ctx.create_horizon(tuples)
+        assert np.abs(got - want).max() < tol, (prec, np.abs(got - want).max())
+        assert np.abs(np.linalg.norm(got, axis=1) - 1).max() < 10 * tol
+        ctx.close()
