@@ -165,8 +165,10 @@ enum {
   RTC_OPT_KERNEL_TIMING = 1, /* record CUDA events around every launch (rtc_stats.ms)                  */
   RTC_OPT_COUNTERS = 2,      /* instrumented traversal (nodes_visited / prims_tested)                  */
   RTC_OPT_MAX_PATHS = 3,     /* size of the path pool (paths in flight, all wavefronts together)        */
-  RTC_OPT_WAVES = 4          /* wavefronts in flight per rtc_render: 2 (default; alternate bands of the frame run on two
+  RTC_OPT_WAVES = 4,         /* wavefronts in flight per rtc_render: 2 (default; alternate bands of the frame run on two
                                 streams, each with half the pool) or 1. RTC_OPT_KERNEL_TIMING implies 1.             */
+  RTC_OPT_REORDER = 5        /* RTC_F32: sort the live queue between bounces by the Morton cell of the ray origins (1) or by cell
+                                and direction octant (2); 0 = off. Same image bit for bit; pays for scenes beyond the L2.   */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------------- */

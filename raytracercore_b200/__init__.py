@@ -9,7 +9,7 @@ _EXPORTS = {
     "Scene": "scene", "LoaderException": "scene",
     "Context": "renderer", "FullRaytracer": "renderer", "RAY_DT": "renderer", "HIT_DT": "renderer",
     "RtcError": "_native", "RTC_F32": "_native", "RTC_F64": "_native", "RTC_OPT_COUNTERS": "_native",
-    "RTC_OPT_KERNEL_TIMING": "_native", "RTC_OPT_MAX_PATHS": "_native", "RTC_OPT_WAVES": "_native",
+    "RTC_OPT_KERNEL_TIMING": "_native", "RTC_OPT_MAX_PATHS": "_native", "RTC_OPT_WAVES": "_native", "RTC_OPT_REORDER": "_native",
     "RTC_BUILDER_SAH": "_native", "RTC_BUILDER_PLOC": "_native",
 }
 __all__ = sorted(_EXPORTS)

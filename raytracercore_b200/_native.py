@@ -20,7 +20,7 @@ RTC_FLAG_MIRROR, RTC_FLAG_TWOSIDED, RTC_FLAG_INVERT, RTC_FLAG_TRANSFORMED, RTC_F
 RTC_CAMERA_FRUSTUM, RTC_CAMERA_ORTHO = 0, 1
 RTC_GEOM_STRIDE, RTC_MATERIAL_STRIDE, RTC_XFORM_STRIDE = 12, 14, 48
 RTC_K_RAYGEN, RTC_K_TRACE, RTC_K_SHADE, RTC_K_COMPACT, RTC_K_ACCUMULATE, RTC_K_COUNT = 0, 1, 2, 3, 4, 5
-RTC_OPT_KERNEL_TIMING, RTC_OPT_COUNTERS, RTC_OPT_MAX_PATHS, RTC_OPT_WAVES = 1, 2, 3, 4
+RTC_OPT_KERNEL_TIMING, RTC_OPT_COUNTERS, RTC_OPT_MAX_PATHS, RTC_OPT_WAVES, RTC_OPT_REORDER = 1, 2, 3, 4, 5
 RTC_BUILDER_SAH, RTC_BUILDER_PLOC = 0, 1
 RTC_BAKED_SEGMENTS = 10
 BAKED_SEGMENT_NAMES = ("nodes", "qnodes", "unbounded", "prims", "mats", "xforms", "aux", "prim_id", "id_to_slot", "sgeom")

@@ -76,6 +76,7 @@ def build(force=False, verbose=False):
         ("kernels_f64.cu", NVCC_COMMON + ["-fmad=false"]),
         ("rtc_api.cu", NVCC_COMMON),
         ("bvh_build.cu", NVCC_COMMON),
+        ("reorder.cu", NVCC_COMMON),
         # Scene.Prepare on the device: bit-identical to the host builder / flatten, hence no FMA contraction here either
         ("prepare_device.cu", NVCC_COMMON + ["-fmad=false"]),
     ]

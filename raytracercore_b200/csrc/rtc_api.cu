@@ -187,6 +187,11 @@ struct rtc_ctx {
   void *d_dir = nullptr, *d_tint = nullptr, *d_hpos = nullptr, *d_hnrm = nullptr, *d_thit = nullptr, *d_radiance = nullptr,
        *d_skip_pos = nullptr;
   uint32_t* d_queue[2] = {nullptr, nullptr};
+  // RTC_OPT_REORDER: a third queue buffer (the sort's output; the three rotate), sort keys and the sort's temporary storage per wave
+  int reorder = 0;
+  uint32_t *d_rqueue = nullptr, *d_rkeys[2] = {nullptr, nullptr};
+  void* d_rtmp[2] = {nullptr, nullptr};
+  size_t rtmp_bytes = 0;
   Control* d_ctl = nullptr;  // [2]: one control block per wavefront in flight
   // Two wavefronts in flight (rtc_render): the bands of a frame alternate between the context's stream and wave_stream, each
   // with its own half of the path pool and its own control block, so that the drain phase of one band's persistent trace
@@ -381,6 +386,11 @@ void free_pool(rtc_ctx* c) {
   free_dev(c->d_hnrm);
   free_dev(c->d_thit);
   for (int i = 0; i < 2; i++) free_dev_t(c->d_queue[i]);
+  free_dev_t(c->d_rqueue);
+  for (int i = 0; i < 2; i++) {
+    free_dev_t(c->d_rkeys[i]);
+    free_dev(c->d_rtmp[i]);
+  }
   free_dev(c->d_radiance);
   free_dev(c->d_skip_pos);
   free_dev_t(c->d_dbg_type);
@@ -408,6 +418,19 @@ int ensure_pool(rtc_ctx* ctx, int64_t want) {
     CU(cudaMemset(ctx->d_ctl, 0, 2 * sizeof(Control)));
   }
   ctx->pool_cap = want;
+  return RTC_OK;
+}
+
+// buffers of the queue re-ordering, sized like the pool
+int ensure_reorder(rtc_ctx* ctx) {
+  if (ctx->d_rqueue) return RTC_OK;
+  const size_t n = (size_t)ctx->pool_cap;
+  CU(cudaMalloc((void**)&ctx->d_rqueue, sizeof(uint32_t) * n));
+  ctx->rtmp_bytes = reorder_temp_bytes((uint32_t)n);
+  for (int i = 0; i < 2; i++) {
+    CU(cudaMalloc((void**)&ctx->d_rkeys[i], sizeof(uint32_t) * n));
+    CU(cudaMalloc(&ctx->d_rtmp[i], std::max<size_t>(ctx->rtmp_bytes, 16)));
+  }
   return RTC_OK;
 }
 
@@ -1190,6 +1213,12 @@ int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb,
   }
   CameraView<R> cv = camera_view<R>(ctx->cam);
   ParamsView<R> par = params_view<R>(ctx->par);
+  uint32_t* spare = nullptr;  // RTC_OPT_REORDER: the third queue buffer of this wave's part of the pool
+  if (ctx->reorder > 0 && ctx->precision == RTC_F32) {
+    int rcr = ensure_reorder(ctx);
+    if (rcr) return rcr;
+    spare = ctx->d_rqueue + pool_offset;
+  }
   {
     Timed t(ctx, RTC_K_RAYGEN, stream);
     CU(Kernels<R>::raygen(cfg, cv, par, band, pv));
@@ -1214,6 +1243,16 @@ int run_band(rtc_ctx* ctx, const Band& band, bool accumulate, double* d_out_rgb,
     {
       Timed t(ctx, RTC_K_COMPACT, stream);
       CU(Kernels<R>::compact(cfg, pv, q, ident));
+    }
+    if constexpr (std::is_same<R, float>::value) {
+      if (ctx->reorder > 0 && i + 1 < bounces && ctx->d_qnodes && !debug) {
+        // the survivors (queue[q ^ 1]) in Morton order of their new origins into the spare buffer, which then takes the
+        // place of queue[q ^ 1]; the unsorted one becomes the spare
+        Timed t(ctx, RTC_K_COMPACT, stream);
+        CU(launch_reorder(stream, (const CNode*)ctx->d_qnodes, pv.hpos, pv.dir, pv.queue[q ^ 1], &pv.ctl->count[q ^ 1], band.n_paths, ctx->reorder,
+                          ctx->d_rkeys[0] + pool_offset, ctx->d_rkeys[1] + pool_offset, spare, ctx->d_rtmp[wave ? 1 : 0], ctx->rtmp_bytes));
+        std::swap(pv.queue[q ^ 1], spare);
+      }
     }
   }
   if (accumulate) {
@@ -1505,6 +1544,10 @@ int rtc_set_option(rtc_ctx* ctx, int option, int64_t value) {
     case RTC_OPT_WAVES:
       if (value < 1 || value > 2) return fail(ctx, RTC_ERR_INVALID, "wavefronts in flight must be 1 or 2");
       ctx->waves = (int)value;
+      return RTC_OK;
+    case RTC_OPT_REORDER:
+      if (value < 0 || value > 2) return fail(ctx, RTC_ERR_INVALID, "queue re-ordering mode must be 0, 1 or 2");
+      ctx->reorder = (int)value;
       return RTC_OK;
     case RTC_OPT_MAX_PATHS:
       if (value < 1024 || value > (int64_t)1 << 28) return fail(ctx, RTC_ERR_INVALID, "max paths must be in [1024, 2^28]");

@@ -297,6 +297,13 @@ size_t flatten_scratch_bytes(int32_t n_nodes, int32_t n_prims);
 int flatten_device(cudaStream_t stream, PrepareArena* arena, int32_t* h_pin, const FlattenInput& in, FlattenOutput& out,
                    std::string& err);  // RTC_OK or an RTC_ERR_* code
 
+// Queue re-ordering between bounces (reorder.cu, f32 mode): queue_out = queue_in[0 .. *count) sorted by the Morton cell of the
+// paths' ray origins on the root node's grid (mode 1) or by cell and direction octant (mode 2); entries beyond *count go last.
+size_t reorder_temp_bytes(uint32_t n);
+cudaError_t launch_reorder(cudaStream_t stream, const CNode* root, const V4<float>* hpos, const V4<float>* dir, const uint32_t* queue_in,
+                           const uint32_t* count, uint32_t n, int mode, uint32_t* keys_in, uint32_t* keys_out, uint32_t* queue_out, void* tmp,
+                           size_t tmp_bytes);
+
 // mode-independent
 // planes -= base (rtc_reduce_accum after an all-reduce: only the samples rendered since then are contributed again)
 cudaError_t launch_subtract_planes(cudaStream_t s, size_t n, double* rgb_sum, uint32_t* samples, uint32_t* misses,

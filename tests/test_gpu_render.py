@@ -498,6 +498,37 @@ def test_two_wavefronts_in_flight_render_the_same_planes():
 
 
 @pytest.mark.gpu
+def test_queue_reordering_between_bounces_renders_the_same_planes():
+    """RTC_OPT_REORDER sorts the live queue by the Morton cell of the ray origins (mode 1) or by cell and direction octant
+    (mode 2) before every bounce after the first. Only the order in which paths are traced and shaded changes: planes, path and
+    ray counts must equal the unsorted render bit for bit, with one and with two wavefronts in flight."""
+    from raytracercore_b200 import RTC_OPT_MAX_PATHS, RTC_OPT_REORDER, RTC_OPT_WAVES
+    sc = Scene.synthetic("spheres", 20000, 0xC4, 0.0)
+    sc.override(width=512, height=384, recursion=5)
+    out = {}
+    for mode, waves in ((0, 1), (1, 1), (2, 1), (1, 2)):
+        ctx = Context(0, RTC_F32)
+        ctx.set_option(RTC_OPT_WAVES, waves)
+        ctx.set_option(RTC_OPT_REORDER, mode)
+        if waves == 2:
+            ctx.set_option(RTC_OPT_MAX_PATHS, 8 << 20)
+        ctx.load(sc, seed=5)
+        ctx.render(0, 48 if waves == 2 else 3)
+        st = ctx.stats()
+        out[(mode, waves)] = (ctx.read_accum(), st.paths, st.rays)
+        ctx.close()
+    for key in ((1, 1), (2, 1)):
+        assert all(np.array_equal(x, y) for x, y in zip(out[(0, 1)][0], out[key][0])), key
+        assert out[(0, 1)][1:] == out[key][1:]
+    ref = Context(0, RTC_F32)
+    ref.set_option(RTC_OPT_WAVES, 1)
+    ref.load(sc, seed=5)
+    ref.render(0, 48)
+    assert all(np.array_equal(x, y) for x, y in zip(ref.read_accum(), out[(1, 2)][0]))
+    ref.close()
+
+
+@pytest.mark.gpu
 def test_create_horizon_on_the_device_against_the_oracle():
     """Vec4D.CreateHorizon (Vec4D.cs:33-58), evaluated directly: the lobe sample around a pole at polar
     cosine z and azimuth theta. f64: the oracle's value to rounding; f32: to 1e-5 (approximate sine / cosine / reciprocal

@@ -20,6 +20,7 @@ ap.add_argument("--precision", default="f32")
 ap.add_argument("--counters", action="store_true")
 ap.add_argument("--max-paths", type=int, default=0)
 ap.add_argument("--waves", type=int, default=0, help="wavefronts in flight (RTC_OPT_WAVES); implies no per-kernel timing")
+ap.add_argument("--reorder", type=int, default=0, help="RTC_OPT_REORDER mode")
 ap.add_argument("--device-bvh", type=int, default=-1, help="build the tree on the GPU with this search radius (0 = default)")
 a = ap.parse_args()
 sc = bench.make_scene(a.workload)
@@ -45,6 +46,9 @@ else:
     print("flatten + upload: %.3f s" % (time.time() - t_build))
     ctx.set_params(sc.params(1))
     ctx.set_camera(sc.camera(None))
+if a.reorder:
+    from raytracercore_b200 import RTC_OPT_REORDER
+    ctx.set_option(RTC_OPT_REORDER, a.reorder)
 ctx.render(0, a.spp)
 ctx.sync()
 ctx.reset_stats()
