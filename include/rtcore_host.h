@@ -52,6 +52,9 @@ int rtcs_scene_bvh(rtcs_scene* s, const rtc_bvh_node** nodes, int32_t* n_nodes, 
 /* AABB.CreateFromBounded of primitive i (AABB.cs:20-36). */
 int rtcs_scene_primitive_bounds(rtcs_scene* s, int32_t i, double bmin[3], double bmax[3]);
 
+/* AABB.CreateFromBounded of primitive i of an ABI scene description, as the builders compute it (general != 0: through a
+ * full Primitive object, the path kept for transformed spheres and planes; the two must agree bit for bit). */
+int rtcs_desc_primitive_bounds(const rtc_scene_desc* scene, int32_t i, int32_t general, double bmin[3], double bmax[3]);
 /* Stand-alone builder over an ABI scene description; nodes must hold 2*n_prims entries. */
 int rtcs_build_bvh(const rtc_scene_desc* scene, int32_t threads, rtc_bvh_node* nodes, int32_t* n_nodes, int32_t* root);
 

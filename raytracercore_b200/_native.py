@@ -146,6 +146,7 @@ SIGNATURES = {
     "rtcs_scene_camera": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Camera)]),
     "rtcs_scene_bvh": (C.c_int, [_P, C.POINTER(C.POINTER(BvhNode)), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rtcs_scene_primitive_bounds": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "rtcs_desc_primitive_bounds": (C.c_int, [C.POINTER(SceneDesc), C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rtcs_build_bvh": (C.c_int, [C.POINTER(SceneDesc), C.c_int32, C.POINTER(BvhNode), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rtcs_raytracer_create": (_P, [_P, C.c_int32, C.c_int32, C.c_uint64, STATUS_FN, _P, C.c_char_p, C.c_int32]),
     "rtcs_raytracer_destroy": (None, [_P]),

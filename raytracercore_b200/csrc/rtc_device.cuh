@@ -1143,17 +1143,19 @@ __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
 #else
 #define RTC_Q8_BOUNDS __launch_bounds__(kTraceThreads, kTraceMinBlocks)
 #endif
-constexpr int kQ8StateWords = 12;  // per-thread cold state after the stack: d.xyz, path, skip code, o.xyz, inv.xyz, norm defect
+constexpr int kQ8StateSlots = 6;  // per-thread cold state in front of the stack, 8 bytes per slot: o.xyz, inv.xyz, d.xyz, norm defect, path, skip code
 
 template <bool COUNT>
 __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io) {
   using R = float;
-  extern __shared__ uint2 s_stack[];  // [sc.q_stack][kTraceThreads] stack entries, then kQ8StateWords x [kTraceThreads] words
-  constexpr uint32_t kStackStride = kTraceThreads * 8u, kCol = kTraceThreads * 4u;
-  // this thread's stack column; its state columns start at sm + state_off
+  // [kQ8StateSlots + sc.q_stack][kTraceThreads] x 8 bytes: first the cold ray state of each thread, two words per slot (one
+  // LDS.64 / STS.64 each), then its stack entries. Every access is this thread's column address `sm` plus an immediate (state)
+  // or plus sp * stride + an immediate (stack): one address register for all of it.
+  extern __shared__ uint2 s_stack[];
+  constexpr uint32_t kStackStride = kTraceThreads * 8u;
   const uint32_t sm = (uint32_t)__cvta_generic_to_shared(s_stack) + threadIdx.x * 8u;
-  const uint32_t st = sm + (uint32_t)sc.q_stack * kStackStride - threadIdx.x * 4u;  // byte address of state word 0
-  enum { S_DX = 0, S_DY, S_DZ, S_PATH, S_SKIP, S_OX, S_OY, S_OZ, S_IX, S_IY, S_IZ, S_DL };
+  enum { S_OXY = 0, S_OZIX, S_IYZ, S_DXY, S_DZL, S_PATHSKIP };  // (o.x, o.y) (o.z, inv.x) (inv.y, inv.z) (d.x, d.y) (d.z, norm defect) (path, skip code)
+  constexpr uint32_t kStackBase = kQ8StateSlots * kStackStride;
   const uint32_t count = *io.count;
   uint32_t n_nodes = 0, n_prims = 0, n_node_steps = 0, n_leaf_steps = 0;
   // lane state in `sp`: >= 0 traversing (= stack depth), kFinished = result not written yet, kEmpty = no ray
@@ -1187,7 +1189,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
       // ---- refill ------------------------------------------------------------------------------------------
       lanes_changed = 1;  // recount after the refill (and keep coming back here once the queue is exhausted)
       if (sp == kFinished) {  // (distance, hit code) in one 8-byte store: position and normal are completed by k_shade
-        const uint32_t fpath = lds32(st + S_PATH * kCol);
+        const uint32_t fpath = lds32(sm + S_PATHSKIP * kStackStride);
         THit<R> th;
         th.t = best.t;
         th.code = best.code;
@@ -1214,18 +1216,12 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
           const uint32_t code = code_of(op.w);
           const V3<R> o = xyz(op), d = xyz(dv);
           const V3<R> inv = mk3(clamped_rcp(d.x), clamped_rcp(d.y), clamped_rcp(d.z));
-          sts32(st + S_DL * kCol, __float_as_uint(dv.w));
-          sts32(st + S_DX * kCol, __float_as_uint(d.x));
-          sts32(st + S_DY * kCol, __float_as_uint(d.y));
-          sts32(st + S_DZ * kCol, __float_as_uint(d.z));
-          sts32(st + S_PATH * kCol, npath);
-          sts32(st + S_SKIP * kCol, code);
-          sts32(st + S_OX * kCol, __float_as_uint(o.x));
-          sts32(st + S_OY * kCol, __float_as_uint(o.y));
-          sts32(st + S_OZ * kCol, __float_as_uint(o.z));
-          sts32(st + S_IX * kCol, __float_as_uint(inv.x));
-          sts32(st + S_IY * kCol, __float_as_uint(inv.y));
-          sts32(st + S_IZ * kCol, __float_as_uint(inv.z));
+          sts64(sm + S_OXY * kStackStride, __float_as_uint(o.x), __float_as_uint(o.y));
+          sts64(sm + S_OZIX * kStackStride, __float_as_uint(o.z), __float_as_uint(inv.x));
+          sts64(sm + S_IYZ * kStackStride, __float_as_uint(inv.y), __float_as_uint(inv.z));
+          sts64(sm + S_DXY * kStackStride, __float_as_uint(d.x), __float_as_uint(d.y));
+          sts64(sm + S_DZL * kStackStride, __float_as_uint(d.z), __float_as_uint(dv.w));
+          sts64(sm + S_PATHSKIP * kStackStride, npath, code);
           Skip<R> sk;
           sk.code = code;
           const uint32_t oct = (rsignbit(d.x) ? 1u : 0u) | (rsignbit(d.y) ? 2u : 0u) | (rsignbit(d.z) ? 4u : 0u);
@@ -1280,7 +1276,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         const uint32_t node = igx + (uint32_t)__popc(imask_g & ((1u << s) - 1u));
         igy &= ~(0x100u << b);
         if ((igy >> 8) != 0) {  // siblings still pending: the group goes to the stack
-          sts64(sm + (uint32_t)sp * kStackStride, igx, igy);
+          sts64(sm + kStackBase + (uint32_t)sp * kStackStride, igx, igy);
           sp++;
         }
         const CNode* np = sc.qnodes + node;
@@ -1295,10 +1291,9 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         const uint32_t imask = em >> 24, lmask = w0[6] & 0xFFu;
         // t = (p + q * step - o) * inv = q * (step * inv) + (p - o) * inv ; q enters as 2^23 + q, so the addend carries
         // -2^23 * step * inv (its rounding is half a grid step: the builder pads every box by one step)
-        const V3<R> ro = mk3(__uint_as_float(lds32(st + S_OX * kCol)), __uint_as_float(lds32(st + S_OY * kCol)),
-                             __uint_as_float(lds32(st + S_OZ * kCol)));
-        const V3<R> ri = mk3(__uint_as_float(lds32(st + S_IX * kCol)), __uint_as_float(lds32(st + S_IY * kCol)),
-                             __uint_as_float(lds32(st + S_IZ * kCol)));
+        const uint2 s0 = lds64(sm + S_OXY * kStackStride), s1 = lds64(sm + S_OZIX * kStackStride), s2 = lds64(sm + S_IYZ * kStackStride);
+        const V3<R> ro = mk3(__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s1.x));
+        const V3<R> ri = mk3(__uint_as_float(s1.y), __uint_as_float(s2.x), __uint_as_float(s2.y));
         const float ax = sx * ri.x, ay = sy * ri.y, az = sz * ri.z;
         const float bx = fmaf(-8388608.0f, ax, (__uint_as_float(w0[0]) - ro.x) * ri.x);
         const float by = fmaf(-8388608.0f, ay, (__uint_as_float(w0[1]) - ro.y) * ri.y);
@@ -1361,12 +1356,12 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
         if (COUNT) n_prims++;
         const PrimRec<R> pr = load_prim(sc, slot);
         Skip<R> sk;
-        sk.code = lds32(st + S_SKIP * kCol);
-        const V3<R> o = mk3(__uint_as_float(lds32(st + S_OX * kCol)), __uint_as_float(lds32(st + S_OY * kCol)),
-                            __uint_as_float(lds32(st + S_OZ * kCol)));
-        const V3<R> d = mk3(__uint_as_float(lds32(st + S_DX * kCol)), __uint_as_float(lds32(st + S_DY * kCol)),
-                            __uint_as_float(lds32(st + S_DZ * kCol)));
-        test_leaf<R>(sc, ref_of(pr), pr, R(0), o, d, __uint_as_float(lds32(st + S_DL * kCol)), sk, src, lds32(st + S_PATH * kCol), best);
+        const uint2 s0 = lds64(sm + S_OXY * kStackStride), s3 = lds64(sm + S_DXY * kStackStride), s4 = lds64(sm + S_DZL * kStackStride),
+                    s5 = lds64(sm + S_PATHSKIP * kStackStride);
+        sk.code = s5.y;
+        const V3<R> o = mk3(__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(lds32(sm + S_OZIX * kStackStride)));
+        const V3<R> d = mk3(__uint_as_float(s3.x), __uint_as_float(s3.y), __uint_as_float(s4.x));
+        test_leaf<R>(sc, ref_of(pr), pr, R(0), o, d, __uint_as_float(s4.y), sk, src, s5.x, best);
       }
     }
     bool done_now = false;
@@ -1374,7 +1369,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
     if (sp >= 0 && (igy >> 8) == 0) {  // the next inner group is fetched even while leaf hits are pending
       if (sp > 0) {
         sp--;
-        const uint2 g = lds64(sm + (uint32_t)sp * kStackStride);
+        const uint2 g = lds64(sm + kStackBase + (uint32_t)sp * kStackStride);
         igx = g.x;
         igy = g.y;
       } else if (((lgy | pgy) >> 8) == 0) {
@@ -1386,7 +1381,7 @@ __global__ void RTC_Q8_BOUNDS k_trace_q8(SceneView<float> sc, TraceIO<float> io)
     if (sp >= 0 && ((lgy | igy) >> 8) == 0) {
       if (sp > 0) {
         sp--;
-        const uint2 g = lds64(sm + (uint32_t)sp * kStackStride);
+        const uint2 g = lds64(sm + kStackBase + (uint32_t)sp * kStackStride);
         igx = g.x;
         igy = g.y;
       } else {
@@ -1961,7 +1956,7 @@ cudaError_t Kernels<R>::horizon(const LaunchCfg& cfg, int64_t n, const double* i
 template <typename R>
 cudaError_t Kernels<R>::trace(const LaunchCfg& cfg, const SceneView<R>& sc, const PathView<R>& pv, int q, bool identity_queue) {
   const size_t smem = Num<R>::is_f64 ? (size_t)sc.q_stack * kTraceThreads * (4 + sizeof(R))
-                                     : (size_t)sc.q_stack * kTraceThreads * sizeof(uint2) + kQ8StateWords * kTraceThreads * sizeof(float);
+                                     : (size_t)(sc.q_stack + kQ8StateSlots) * kTraceThreads * sizeof(uint2);
   // Function attributes and occupancy are per (device, kernel) for the whole process, whatever thread launches: the largest
   // dynamic shared-memory size asked for so far is kept per device (raised, never lowered: a smaller launch is always legal
   // under a larger limit) and the resident-CTA count per (device, size), under one mutex.

@@ -151,6 +151,15 @@ int rtcs_scene_primitive_bounds(rtcs_scene* s, int32_t i, double bmin[3], double
   return RTC_OK;
 }
 
+int rtcs_desc_primitive_bounds(const rtc_scene_desc* d, int32_t i, int32_t general, double bmin[3], double bmax[3]) {
+  if (!d || !bmin || !bmax || i < 0 || i >= d->n_prims) return RTC_ERR_INVALID;
+  if (general)
+    DescPrimitiveBoundsGeneral(*d, i, bmin, bmax);
+  else
+    DescPrimitiveBounds(*d, i, bmin, bmax);
+  return RTC_OK;
+}
+
 int rtcs_build_bvh(const rtc_scene_desc* d, int32_t threads, rtc_bvh_node* nodes, int32_t* n_nodes, int32_t* root) {
   if (!d || !nodes || !n_nodes || !root || d->n_prims < 0) return RTC_ERR_INVALID;
   int n = d->n_prims;

@@ -179,7 +179,58 @@ static void PrimitiveFromDesc(const rtc_scene_desc& d, int i, Primitive& p) {
   }
 }
 
+// The two common cases of DescPrimitiveBounds written out: the same operations on the same values as PrimitiveBounds over
+// GetCenter / GetMaxCenterDistance above (a Dot with a signed unit vector is the signed component: the other products are
+// zeros), without building a Primitive. Anything else -- transformed spheres, planes, non-finite input -- takes the general
+// path; tests/test_bvh_builder.py compares the two on every kind.
+static bool FastBounds(const rtc_scene_desc& d, int i, double bmin[3], double bmax[3]) {
+  const double* g = d.geom + (size_t)i * RTC_GEOM_STRIDE;
+  const uint8_t kind = d.kind[i], f = d.flags[i];
+  if (kind == RTC_KIND_TRIANGLE) {
+    for (int k = 0; k < 9; k++)
+      if (!std::isfinite(g[k])) return false;
+    const bool mirror = f & RTC_FLAG_MIRROR;
+    double v3[3] = {0, 0, 0}, c[3];
+    for (int k = 0; k < 3; k++) {
+      const double v0 = g[k], v1 = g[k] + g[3 + k], v2 = g[k] + g[6 + k];
+      c[k] = ((v0 + v1) + v2) / 3;  // Triangle.cs:226-229
+      if (mirror) v3[k] = ((g[k] + g[3 + k]) + g[6 + k]) - c[k];
+    }
+    const bool use_v3 = !(v3[0] == 0 && v3[1] == 0 && v3[2] == 0);  // `v3 != Vec4D()`
+    for (int k = 0; k < 3; k++) {
+      const double a0 = g[k] - c[k], a1 = (g[k] + g[3 + k]) - c[k], a2 = (g[k] + g[6 + k]) - c[k];
+      double dn = std::fmax(-a0, 0.0), dp = std::fmax(a0, 0.0);
+      dn = std::fmax(-a1, dn);
+      dp = std::fmax(a1, dp);
+      dn = std::fmax(-a2, dn);
+      dp = std::fmax(a2, dp);
+      if (use_v3) {
+        dn = std::fmax(-v3[k], dn);
+        dp = std::fmax(v3[k], dp);
+      }
+      bmin[k] = std::nextafter(c[k] - dn, -std::numeric_limits<double>::infinity());
+      bmax[k] = std::nextafter(c[k] + dp, std::numeric_limits<double>::infinity());
+    }
+    return true;
+  }
+  if (kind == RTC_KIND_SPHERE && !((f & RTC_FLAG_TRANSFORMED) && d.xform && d.xform[i] >= 0)) {
+    for (int k = 0; k < 4; k++)
+      if (!std::isfinite(g[k])) return false;
+    for (int k = 0; k < 3; k++) {  // Sphere.cs:212-232
+      bmin[k] = g[k] - g[3];
+      bmax[k] = g[k] + g[3];
+    }
+    return true;
+  }
+  return false;
+}
+
 void DescPrimitiveBounds(const rtc_scene_desc& d, int i, double bmin[3], double bmax[3]) {
+  if (FastBounds(d, i, bmin, bmax)) return;
+  DescPrimitiveBoundsGeneral(d, i, bmin, bmax);
+}
+
+void DescPrimitiveBoundsGeneral(const rtc_scene_desc& d, int i, double bmin[3], double bmax[3]) {
   static thread_local Primitive p;
   PrimitiveFromDesc(d, i, p);
   PrimitiveBounds(p, bmin, bmax);

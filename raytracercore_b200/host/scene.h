@@ -127,6 +127,8 @@ void PrimitiveBounds(const Primitive& p, double bmin[3], double bmax[3]);
 // Leaf box from the flattened description alone (the ABI carries Vert0/Edge0to1/Edge0to2, not Vert1/Vert2, so
 // triangle boxes are rebuilt from v0, v0+e1, v0+e2 and widened by one ulp to stay conservative).
 void DescPrimitiveBounds(const rtc_scene_desc& d, int i, double bmin[3], double bmax[3]);
+// the same through a full Primitive (what DescPrimitiveBounds falls back to for transformed spheres and planes)
+void DescPrimitiveBoundsGeneral(const rtc_scene_desc& d, int i, double bmin[3], double bmax[3]);
 // Replacement for BVH.Construct (BVH.cs:50-236): binned-SAH tree with exactly one primitive per leaf
 // (BVH.cs:256-264) over the n leaf boxes (bmin/bmax: n*3). Primitives with infinite boxes (planes) are chained
 // above the root. Nodes come out in reference shape; returns the root index (-1 for n == 0).

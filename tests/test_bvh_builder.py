@@ -78,3 +78,46 @@ def test_single_primitive_and_empty_scene():
     assert len(nodes) == 1 and root == 0 and nodes[0]["prim"] == 0
     nodes, root = Scene.from_string("size 4 4\n").bvh_array()
     assert len(nodes) == 0 and root == -1
+
+
+def test_fast_bounds_equal_the_general_path_bit_for_bit():
+    """DescPrimitiveBounds writes the triangle / plain-sphere cases out; every box must equal the one computed through a full
+    Primitive (GetCenter / GetMaxCenterDistance), on the reference scenes, on synthetic soups and sphere fields, on parallelograms,
+    on degenerate and on far-from-origin triangles, and non-finite input must take the general path."""
+    import ctypes as C
+
+    from raytracercore_b200 import _native as N
+
+    def both(sc):
+        d = sc.desc()
+        out = np.zeros((2, d.n_prims, 6))
+        for general in (0, 1):
+            lo, hi = (C.c_double * 3)(), (C.c_double * 3)()
+            for i in range(d.n_prims):
+                assert N.lib.rtcs_desc_primitive_bounds(C.byref(d), i, general, lo, hi) == 0
+                out[general, i, :3], out[general, i, 3:] = lo[:], hi[:]
+        return out
+
+    rng = np.random.default_rng(4)
+    tris = "".join("vertex %s %s %s\n" % tuple(repr(float(c)) for c in v) for v in np.concatenate([
+        rng.uniform(-1, 1, (60, 3)), rng.uniform(-1, 1, (30, 3)) * 1e6 + 1e9, rng.uniform(-1, 1, (30, 3)) * 1e-9, np.zeros((3, 3))]))
+    text = "twosided true\n" + tris + "".join("tri %d %d %d%s\n" % (3 * k, 3 * k + 1, 3 * k + 2, " mirrored" if k % 3 == 0 else "") for k in range(41))
+    text += "sphere 1 2 3 .5\npushtransform\nscale 2 1 1\nrotate 1 2 3 40\nsphere 0 0 0 1\npoptransform\nplane 1 0 0 1\nplane 1 1 1 1\n"
+    scenes = [Scene.from_string(text), Scene.from_file(os.path.join(SCENES, "cornell_bounce.scene")), Scene.from_file(os.path.join(SCENES, "die.scene")),
+              Scene.synthetic("soup", 3000, 7, 0.05), Scene.synthetic("spheres", 2000, 9, 0.0)]
+    for sc in scenes:
+        a = both(sc)
+        assert a[0].tobytes() == a[1].tobytes()
+    # non-finite geometry: same (non-finite) answer through the general path
+    # (the loader rejects `inf`: the description is patched by hand)
+    keep = Scene.synthetic("soup", 4, 1, 0.05)  # (the description points into the scene's own arrays)
+    d = keep.desc()
+    geom = np.ctypeslib.as_array(d.geom, shape=(4 * 12,))
+    geom[0] = np.inf
+    geom[12 + 3] = np.nan
+    lo, hi, lo2, hi2 = ((C.c_double * 3)() for _ in range(4))
+    for i in range(2):
+        N.lib.rtcs_desc_primitive_bounds(C.byref(d), i, 0, lo, hi)
+        N.lib.rtcs_desc_primitive_bounds(C.byref(d), i, 1, lo2, hi2)
+        assert np.array_equal(np.array(lo[:] + hi[:]), np.array(lo2[:] + hi2[:]), equal_nan=True)
+        assert not np.isfinite(np.array(lo[:] + hi[:])).all()
