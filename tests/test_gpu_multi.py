@@ -85,7 +85,9 @@ def test_reduced_frames_equal_the_single_gpu_render(root):
 def test_scene_broadcast_over_nvlink_gives_every_rank_the_roots_scene():
     """rtc_bcast_scene: only rank 0 prepares and uploads the scene; the other ranks receive the device image with ncclBroadcast
     and, given the same camera and parameters, must render bit-identical planes -- for a scene that replaces an earlier one
-    of a different size on the receivers as well. A receiving context has no host-side description (rtc_bake fails)."""
+    of a different size on the receivers as well, and whether the root prepared the scene on the host or on the device
+    (rtc_prepare_device). A receiving context has no host-side description, but rtc_bake reads its device image back: byte for
+    byte the root's."""
     n_dev = N.lib.rtc_device_count()
     if n_dev < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -97,19 +99,22 @@ def test_scene_broadcast_over_nvlink_gives_every_rank_the_roots_scene():
     uid = Context.comm_unique_id()
     ctxs = [Context(r, RTC_F32) for r in range(world)]
     got = [[None] * len(scenes) for _ in range(world)]
+    images = [[None] * len(scenes) for _ in range(world)]
 
     def rank_main(r):
+        from raytracercore_b200 import RTC_BUILDER_SAH
         c = ctxs[r]
         c.comm_init(world, r, uid)
         for k, sc in enumerate(scenes):
             if r == 0:
-                c.load(sc, seed=4)
+                c.load(sc, seed=4, device_prepare=RTC_BUILDER_SAH if k == 1 else None)
             c.bcast_scene(0)
             if r != 0:
                 c.set_params(sc.params(4))
                 c.set_camera(sc.camera())
-                with pytest.raises(N.RtcError):
-                    c.bake()
+            b = c.bake()
+            images[r][k] = b.segments()
+            b.close()
             c.clear_accum()
             c.render(0, 2)
             got[r][k] = c.read_accum()
@@ -118,6 +123,7 @@ def test_scene_broadcast_over_nvlink_gives_every_rank_the_roots_scene():
     for k in range(len(scenes)):
         for r in range(1, world):
             assert all(np.array_equal(a, b) for a, b in zip(got[r][k], got[0][k])), (k, r)
+            assert images[r][k] == images[0][k], (k, r)
         assert got[0][k][1].any()
     for c in ctxs:
         c.close()
