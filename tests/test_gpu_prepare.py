@@ -206,3 +206,32 @@ def test_full_size_soup_prepares_on_the_device_like_on_the_host():
     assert_images_equal(image(host), image(dev), "soup1m")
     host.close()
     dev.close()
+
+
+def test_prepare_device_error_behaviour():
+    """Same conventions as the host path: an error code and a text, never a crash; the context stays usable."""
+    from raytracercore_b200 import RtcError
+    ctx = Context(0, RTC_F32)
+    with pytest.raises(RtcError) as e:
+        ctx.prepare_device(RTC_BUILDER_SAH)  # no scene yet
+    assert e.value.code == N.RTC_ERR_STATE
+    sc = make_scene("mixed")
+    ctx.upload_scene(sc)
+    with pytest.raises(RtcError) as e:
+        ctx.prepare_device(7)  # unknown builder
+    assert e.value.code == N.RTC_ERR_INVALID
+    with pytest.raises(RtcError):
+        ctx.bake()  # nothing prepared yet
+    ctx.prepare_device(RTC_BUILDER_SAH)
+    ctx.set_params(sc.params(1))
+    ctx.set_camera(sc.camera())
+    ctx.render(0, 1)
+    rgb, s, m = ctx.read_accum()
+    assert np.all(s + m == 1)
+    # a new scene invalidates the tree (Scene.AddPrimitive -> ResetAccelerator, Scene.cs:58-63)
+    ctx.upload_scene(make_scene("single"))
+    with pytest.raises(RtcError):
+        ctx.render(1, 1)
+    with pytest.raises(RtcError):
+        ctx.get_bvh()
+    ctx.close()
