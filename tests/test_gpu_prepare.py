@@ -235,3 +235,34 @@ def test_prepare_device_error_behaviour():
     with pytest.raises(RtcError):
         ctx.get_bvh()
     ctx.close()
+
+
+def test_random_small_scenes_with_tied_centroids():
+    """Many small scenes of spheres and triangles on a coarse lattice (equal centroids, equal bin boundaries, every size from 1
+    to 40 and a few larger ones): the device tree and image must equal the host path's on each -- the median fall-back, the
+    ordering pass and the two-primitive split all decide ties by primitive ID."""
+    rng = np.random.default_rng(2024)
+    hdr = "size 8 8\ncamera 0 0 -9 0 0 0 0 1 0 40\ntwosided true\n"
+    sizes = list(range(1, 41)) + [63, 64, 65, 127, 128, 129, 257, 500]
+    host, dev = Context(0, RTC_F32), Context(0, RTC_F32)
+    for n in sizes:
+        lines = []
+        nv = 0
+        for i in range(n):
+            c = rng.integers(0, 4, 3)  # 64 lattice sites: many primitives share a centroid
+            if rng.random() < 0.6:
+                lines.append("sphere %d %d %d %s\n" % (c[0], c[1], c[2], ("0.25", "0.5")[int(rng.integers(0, 2))]))
+            else:
+                lines.append("vertex %d %d %d\nvertex %d.5 %d %d\nvertex %d %d.5 %d\ntri %d %d %d\n" % (c[0], c[1], c[2], c[0], c[1], c[2], c[0], c[1], c[2], nv, nv + 1, nv + 2))
+                nv += 3
+        if n % 7 == 0:
+            lines.insert(n // 2, "plane 0 0 1 5\n")
+        sc = Scene.from_string(hdr + "".join(lines))
+        for ctx in (host, dev):
+            ctx.upload_scene(sc)
+        host.build_bvh()
+        dev.prepare_device(RTC_BUILDER_SAH)
+        assert tree_bytes(host) == tree_bytes(dev), n
+        assert_images_equal(image(host), image(dev), "lattice scene of %d primitives" % n)
+    host.close()
+    dev.close()
