@@ -183,9 +183,12 @@ namespace RaytracerCore.Raytracing.Gpu
 			UpdateDebugCallback = updateDebug;
 			int device = 0;
 			int.TryParse(Environment.GetEnvironmentVariable("RTCORE_DEVICE"), out device);
-			uint spp = 4;
-			uint.TryParse(Environment.GetEnvironmentVariable("RTCORE_SAMPLES_PER_PASS"), out spp);
-			SamplesPerPass = Math.Max(1u, spp);
+			// samples per pass: RTCORE_SAMPLES_PER_PASS, else passes of about 8 Mi paths (what keeps both wavefronts of rtc_render busy
+			// while a pass still ends, and Stop / Pause / the status line are served, every few tens of milliseconds)
+			uint spp;
+			if (!uint.TryParse(Environment.GetEnvironmentVariable("RTCORE_SAMPLES_PER_PASS"), out spp) || spp == 0)
+				spp = (uint)Math.Min(64.0, Math.Max(1.0, Math.Ceiling((double)(8u << 20) / Math.Max(1.0, (double)scene.Width * scene.Height))));
+			SamplesPerPass = spp;
 			RtcoreNative.Check(IntPtr.Zero, RtcoreNative.rtc_create(device, RtcoreNative.F32, out Ctx));
 			DebugPathtracer = new GpuDebugPathtracer(this);
 			DebugRaycaster = new GpuDebugRaycaster(this, scene);

@@ -5,8 +5,10 @@
 // GetSampleSet :131, GetBitmap :179, Exposure :36). The worker threads, tile cursor and ConcurrentQueue of the
 // reference (:271-344) are replaced by GPU sample passes over the whole image; the 100 ms status loop becomes one
 // status callback per pass.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -139,7 +141,12 @@ void rtcs_raytracer_destroy(rtcs_raytracer* r) {
 
 int rtcs_raytracer_start(rtcs_raytracer* r, uint32_t samples_per_pass, uint32_t max_samples) {
   if (!r) return RTC_ERR_INVALID;
-  if (samples_per_pass == 0) samples_per_pass = 1;
+  if (samples_per_pass == 0) {
+    // automatic: passes of about 8 Mi paths -- what keeps the two wavefronts of rtc_render busy while a pass
+    // still ends, and Stop / Pause / the status line are served, every few tens of milliseconds
+    const double pixels = std::max(1.0, (double)r->scene->Width * (double)r->scene->Height);
+    samples_per_pass = (uint32_t)std::min(64.0, std::max(1.0, std::ceil((double)(8u << 20) / pixels)));
+  }
   {
     std::unique_lock<std::mutex> lk(r->state_mutex);
     r->state_cv.wait(lk, [&] { return !r->Running.load(); });  // `while (Running) ;` FullRaytracer.cs:245

@@ -238,6 +238,10 @@ def test_full_raytracer_mirror():
     assert rt.GetSampleSet(10 ** 6, -5)[1:] == rt.GetSampleSet(63, 0)[1:]  # clamped like FullRaytracer.cs:137-138
     bmp = rt.GetBitmap()
     assert bmp.shape == (48, 64) and (bmp >> 24).max() == 255
+    # automatic pass size: about 8 Mi paths per pass, at most 64 samples (64 x 48 pixels: 64)
+    log.clear()
+    rt.Start(samples_per_pass=0, max_samples=100)
+    assert len(log) == 4 and " 64.00/px " in log[2][0] and " 100.00/px " in log[3][0]
     # background thread + Pause / Resume / Stop handshake
     t = threading.Thread(target=lambda: rt.Start(samples_per_pass=1))
     t.start()
