@@ -1766,7 +1766,7 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
   // table, and the work arrays of the builder and of the flatten (which run one after the other and share their part).
   const size_t nz = (size_t)n;
   const int32_t nn_max = 2 * n;  // (2m - 1 + 2 (n - m) <= 2n)
-  const size_t fixed_bytes = nz * 6 * sizeof(double) * 2 + nz * sizeof(int32_t) * 2 + (f32 ? nz * sizeof(StagedPrim) : 0) + 16 * 256;
+  const size_t fixed_bytes = nz * 6 * sizeof(double) + nz * sizeof(int32_t) * 2 + (f32 ? nz * sizeof(StagedPrim) : 0) + 16 * 256;
   const size_t work_bytes = std::max(build_bvh_sah_scratch_bytes(n), f32 ? flatten_scratch_bytes(nn_max, n) : (size_t)0);
   PrepareArena arena;
   CU(cudaMalloc((void**)&arena.base, fixed_bytes + work_bytes));
@@ -1790,7 +1790,6 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
     return p;
   };
   double* d_allboxes = (double*)carve(nz * 6 * sizeof(double));
-  double* d_boxes_c = (double*)carve(nz * 6 * sizeof(double));  // compacted (bounded only); unused when every primitive is bounded
   int32_t* d_ids = (int32_t*)carve(nz * sizeof(int32_t));
   int32_t* d_slot_prim = (int32_t*)carve(nz * sizeof(int32_t));
   StagedPrim* d_staged = f32 ? (StagedPrim*)carve(nz * sizeof(StagedPrim)) : nullptr;
@@ -1837,6 +1836,9 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
       }
       ids.push_back(i);
     }
+    // the bounded primitives' boxes, compacted: out of the work area (scenes with planes only; the builder's pool allocates
+    // on its own what no longer fits)
+    double* d_boxes_c = (double*)carve((size_t)m * 6 * sizeof(double));
     CU(cudaMemcpyAsync(d_ids, ids.data(), (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     cudaError_t e = launch_gather_boxes(ctx->stream, m, d_ids, d_allboxes, d_boxes_c);
     if (e != cudaSuccess) return fail(ctx, RTC_ERR_CUDA, std::string("gather boxes: ") + cudaGetErrorString(e));
@@ -1859,6 +1861,11 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
     return fail(ctx, code, msg);
   };
 
+#define BCK(call)                                                                                    \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) return bail(RTC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
   // the records travel on the copy stream, staged by a second host thread (float conversion and material packing on the host
   // threads, through the same pinned ring) while this thread drives the level-synchronous build; the records kernel at the very
   // end is the only reader
@@ -1896,14 +1903,14 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
     } else {
       std::vector<double> boxes((size_t)m * 6);
       std::vector<int32_t> pid(m);
-      CU(cudaMemcpyAsync(boxes.data(), d_boxes, boxes.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
+      BCK(cudaMemcpyAsync(boxes.data(), d_boxes, boxes.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      BCK(cudaStreamSynchronize(ctx->stream));
       for (int32_t i = 0; i < m; i++) pid[i] = ids.empty() ? i : ids[i];
       std::vector<rtc_bvh_node> hn((size_t)2 * m - 1);
       cudaError_t e = build_bvh_ploc(ctx->stream, m, boxes.data(), pid.data(), radius, hn.data(), &root, &levels);
       if (e != cudaSuccess) return bail(RTC_ERR_CUDA, std::string("build_bvh_ploc: ") + cudaGetErrorString(e));
-      CU(cudaMemcpyAsync(d_bn, hn.data(), hn.size() * sizeof(rtc_bvh_node), cudaMemcpyHostToDevice, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
+      BCK(cudaMemcpyAsync(d_bn, hn.data(), hn.size() * sizeof(rtc_bvh_node), cudaMemcpyHostToDevice, ctx->stream));
+      BCK(cudaStreamSynchronize(ctx->stream));
     }
   }
   if (nu > 0) {  // the chain of unbounded leaves above the root (bvh_builder.cpp: BuildBVH), first plane outermost-left
@@ -1911,8 +1918,8 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
     rtc_bvh_node top;
     std::memset(&top, 0, sizeof(top));
     if (root >= 0) {
-      CU(cudaMemcpyAsync(&top, d_bn + root, sizeof(top), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
+      BCK(cudaMemcpyAsync(&top, d_bn + root, sizeof(top), cudaMemcpyDeviceToHost, ctx->stream));
+      BCK(cudaStreamSynchronize(ctx->stream));
     }
     int32_t next = m > 0 ? 2 * m - 1 : 0;
     const int32_t chain_begin = next;
@@ -1945,8 +1952,8 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
       root = next + 1;
       next += 2;
     }
-    CU(cudaMemcpyAsync(d_bn + chain_begin, chain.data(), chain.size() * sizeof(rtc_bvh_node), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    BCK(cudaMemcpyAsync(d_bn + chain_begin, chain.data(), chain.size() * sizeof(rtc_bvh_node), cudaMemcpyHostToDevice, ctx->stream));
+    BCK(cudaStreamSynchronize(ctx->stream));
   }
   ctx->root = root;
   st.build_levels = levels;
@@ -2018,7 +2025,7 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
     unb_refs.push_back(prep::leaf_ref_of(ctx->kind[p], ctx->flags[p], ctx->xform[p], (uint32_t)(fout.n_bounded + (int32_t)r)));
   }
   if (!unb_refs.empty())
-    CU(cudaMemcpyAsync(ctx->d_unbounded, unb_refs.data(), unb_refs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    BCK(cudaMemcpyAsync(ctx->d_unbounded, unb_refs.data(), unb_refs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   std::vector<DXform<float>> dx(std::max(1, ctx->n_xforms));
   std::memset(dx.data(), 0, dx.size() * sizeof(DXform<float>));
   for (int32_t j = 0; j < ctx->n_xforms; j++) {
@@ -2036,8 +2043,8 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
         const double* x = &ctx->xforms[(size_t)j * RTC_XFORM_STRIDE];
         for (int k2 = 0; k2 < 3; k2++) dx[j].r[k2] = V4<float>{(float)x[k2 * 3], (float)x[k2 * 3 + 1], (float)x[k2 * 3 + 2], 0.0f};
       }
-  CU(cudaMemcpyAsync(ctx->d_xforms, dx.data(), dx.size() * sizeof(DXform<float>), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  BCK(cudaMemcpyAsync(ctx->d_xforms, dx.data(), dx.size() * sizeof(DXform<float>), cudaMemcpyHostToDevice, ctx->stream));
+  BCK(cudaStreamSynchronize(ctx->stream));
   ctx->n_unbounded = nu;
   ctx->root_node = 0;
   ctx->bvh_depth = fout.depth;
@@ -2059,6 +2066,7 @@ int rtc_prepare_device(rtc_ctx* ctx, int32_t builder, int32_t radius, rtc_prepar
                          "%d wide nodes, depth %d\n", n, st.boxes_ms, st.build_ms, levels, st.flatten_ms, st.total_ms, fout.n_qnodes, fout.depth);
   return RTC_OK;
 }
+#undef BCK
 
 int rtc_bake(rtc_ctx* ctx, rtc_baked** out) {
   if (!ctx || !out) return RTC_ERR_INVALID;
