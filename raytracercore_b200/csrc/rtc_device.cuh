@@ -1724,7 +1724,10 @@ __global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(
         R w;
         set_code(w, code);
         st4(&io.hpos[path], pos.x, pos.y, pos.z, F64 ? hit_t : w);
-        st4(&io.hnrm[path], normal.x, normal.y, normal.z, w);
+        // the skip hit's normal: the f32 traversal reads it only for the positional self-hit rule of spheres (a flat primitive equal
+        // to the skip primitive is always the self-hit, and the skip code travels in hpos.w): 16 bytes per survivor not written
+        const uint32_t hk = (code >> HIT_KIND_SHIFT) & 3u;
+        if (F64 || io.dbg_type || hk == DK_SPHERE || hk == DK_XSPHERE) st4(&io.hnrm[path], normal.x, normal.y, normal.z, w);
       }
     }
     if (io.dbg_type) {
