@@ -797,6 +797,10 @@ constexpr int kStreamThreads = 256;
 #ifndef RTC_TRACE_MIN_BLOCKS
 #define RTC_TRACE_MIN_BLOCKS 7
 #endif
+#ifndef RTC_SHADE_THREADS
+#define RTC_SHADE_THREADS 256
+#endif
+constexpr int kShadeThreads = RTC_SHADE_THREADS;
 #ifndef RTC_SHADE_MIN_BLOCKS
 #define RTC_SHADE_MIN_BLOCKS 3
 #endif
@@ -1550,7 +1554,7 @@ __device__ __forceinline__ void complete_hit(const SceneView<R>& sc, uint32_t co
 // queue by a warp-aggregated stream compaction (ballot + popc + one atomicAdd per warp) -- the loop's `break`/`return` of
 // the reference.
 template <typename R>
-__global__ void __launch_bounds__(kStreamThreads, RTC_SHADE_MIN_BLOCKS) k_shade(SceneView<R> sc, ParamsView<R> par, Band band, ShadeIO<R> io,
+__global__ void __launch_bounds__(kShadeThreads, RTC_SHADE_MIN_BLOCKS) k_shade(SceneView<R> sc, ParamsView<R> par, Band band, ShadeIO<R> io,
                                                            int bounce) {
   constexpr bool F64 = Num<R>::is_f64;
   const uint32_t count = *io.count;
@@ -2031,7 +2035,7 @@ cudaError_t Kernels<R>::shade(const LaunchCfg& cfg, const SceneView<R>& sc, cons
   io.count_out = &pv.ctl->count[q ^ 1];
   io.dbg_type = pv.dbg_type;
   io.dbg_fresnel = pv.dbg_fresnel;
-  k_shade<R><<<grid, kStreamThreads, 0, cfg.stream>>>(sc, par, band, io, bounce);
+  k_shade<R><<<grid * (kStreamThreads / kShadeThreads), kShadeThreads, 0, cfg.stream>>>(sc, par, band, io, bounce);
   return cudaGetLastError();
 }
 
