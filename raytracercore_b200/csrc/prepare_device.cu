@@ -944,4 +944,32 @@ int flatten_device(cudaStream_t stream, PrepareArena* arena, int32_t* h_pin, con
 #undef FCU
 }
 
+// With lazy module loading the first launch of every kernel pays for loading it (a millisecond or so each, ~30 kernels here and in
+// CUB): that is a cost of starting the process, not of Scene.Prepare, so rtc_create asks for the kernels' attributes once per
+// device, which loads them.
+void prepare_device_preload() {
+  cudaFuncAttributes a;
+  const void* fns[] = {(const void*)k_sb_init,      (const void*)k_seg_reset,  (const void*)k_seg_bounds,  (const void*)k_seg_prepare,
+                       (const void*)k_bins_init,    (const void*)k_bin,        (const void*)k_sah,         (const void*)k_level_total,
+                       (const void*)k_sortkey,      (const void*)k_side,       (const void*)k_scatter,     (const void*)k_children,
+                       (const void*)k_union_level,  (const void*)k_single_leaf, (const void*)k_gather_boxes, (const void*)k_bfs,
+                       (const void*)k_up,           (const void*)k_rank,       (const void*)k_unb_fetch,   (const void*)k_resolve_root,
+                       (const void*)k_wide_a,       (const void*)k_wide_b,     (const void*)k_records};
+  for (const void* f : fns) cudaFuncGetAttributes(&a, f);
+  // the three scans the passes use (u32, i32, u64), on one element each
+  void* buf = nullptr;
+  if (cudaMalloc(&buf, 4096) == cudaSuccess) {
+    char* b = (char*)buf;
+    size_t tb = 2048;
+    cub::DeviceScan::ExclusiveSum(b + 2048, tb, (uint32_t*)b, (uint32_t*)(b + 64), 1);
+    tb = 2048;
+    cub::DeviceScan::ExclusiveSum(b + 2048, tb, (int32_t*)b, (int32_t*)(b + 64), 1);
+    tb = 2048;
+    cub::DeviceScan::ExclusiveSum(b + 2048, tb, (unsigned long long*)b, (unsigned long long*)(b + 64), 1);
+    cudaDeviceSynchronize();
+    cudaFree(buf);
+  }
+  cudaGetLastError();
+}
+
 }  // namespace rtc

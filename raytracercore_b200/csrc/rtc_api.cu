@@ -1468,6 +1468,15 @@ int rtc_create(int device, int precision, rtc_ctx** out) {
     return RTC_ERR_CUDA;
   }
   ctx->own_stream = ctx->stream;
+  {  // once per device: load the kernels of Scene.Prepare (lazy module loading would otherwise bill the first prepare for it)
+    static std::mutex mu;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> g(mu);
+    if (std::find(done.begin(), done.end(), device) == done.end()) {
+      prepare_device_preload();
+      done.push_back(device);
+    }
+  }
   *out = ctx;
   return RTC_OK;
 }

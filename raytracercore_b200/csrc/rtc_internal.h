@@ -268,6 +268,7 @@ static_assert(sizeof(StagedPrim) == 96, "StagedPrim layout");
 // The host builder's binned-SAH tree (host/bvh_builder.cpp), node for node, over m bounded primitives: d_boxes m x (lo[3],
 // hi[3]) f64 leaf boxes, d_prim_ids their primitive IDs (ascending; null = identity), d_nodes room for 2m-1 nodes (root =
 // node 0). h_pin: 8 x int32 of pinned host memory. Synchronises `stream`.
+void prepare_device_preload();  // loads this unit's kernels (rtc_create, once per device)
 size_t build_bvh_sah_scratch_bytes(int32_t m);
 cudaError_t build_bvh_sah_device(cudaStream_t stream, PrepareArena* arena, int32_t* h_pin, int32_t m, const double* d_boxes,
                                  const int32_t* d_prim_ids, rtc_bvh_node* d_nodes, int32_t* levels_out);
