@@ -13,7 +13,7 @@ PCIe upload on rank 0, then rtc_bcast_scene over NVLink), render, reduce, read-b
 
 Besides the headline workload (BASELINE C3, the configuration the north-star ratio is quoted on) the one JSON line carries
 `c5`: the 10 M-triangle scene at 3840x2160 (BASELINE C5, the configuration BASELINE quotes at 1/2/4/8 GPUs) in a weak- and a
-strong-scaling form, and at N = 1 `per_scene`: short runs of the other BASELINE configs.
+strong-scaling form, and `per_scene`: short runs of the other BASELINE configs at the same N.
 """
 import argparse
 import json
@@ -591,10 +591,11 @@ def main():
         j5.close()
         del j5
 
-    # ---------------- the other BASELINE configs (N = 1) ----------------
-    if world == 1 and not args.no_other_scenes:
-        # BASELINE.json quotes the metric "per scene": short device-resident runs of the other configs (3 warm-up + 4
-        # timed steps each, CUDA events on the launching stream), reported beside the headline workload
+    # ---------------- the other BASELINE configs, at N ranks like everything else ----------------
+    if not args.no_other_scenes:
+        # BASELINE.json quotes the metric "per scene at 1/2/4/8": short device-resident runs of the other configs (3 warm-up + 4
+        # timed steps each, CUDA events on the launching stream, max over ranks; N > 1: weak scaling -- every rank adds its own
+        # sample range of every frame, one reduce per frame), reported beside the headline workload
         per_scene = {}
         for w in ("bounce", "die", "spheres100k", "soup1m"):
             if w == args.workload:
@@ -603,9 +604,12 @@ def main():
             j2 = Job(env, w, prec)
             r2 = j2.timed(wl2["spp"], 4, 3)
             per_scene[w] = {"value": r2["value"], "unit": "Mrays/s", "spp_mpix_per_s": r2["paths"] / (r2["ms"] * 1e-3) / 1e6,
-                            "ms_per_step": r2["ms_per_step"], "description": wl2["desc"], "spp_per_step": wl2["spp"], "n_prims": j2.n_prims}
+                            "ms_per_step": r2["ms_per_step"], "description": wl2["desc"], "spp_per_step_per_gpu": wl2["spp"], "n_prims": j2.n_prims,
+                            "n_gpus": world, "scaling": "weak"}
             j2.close()
-        line["per_scene"] = per_scene
+            del j2
+        if rank == 0:
+            line["per_scene"] = per_scene
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
