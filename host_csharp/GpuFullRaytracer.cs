@@ -28,6 +28,7 @@ using System;
 using System.Collections.Generic;
 using System.Drawing;
 using System.Drawing.Imaging;
+using System.Linq;
 using System.Reflection;
 using System.Threading;
 using RaytracerCore.Raytracing.Acceleration;
@@ -73,8 +74,8 @@ namespace RaytracerCore.Raytracing.Gpu
 	}
 
 	/// <summary>DebugRaycaster (Raytracing/DebugRaycaster.cs) with the per-pixel queries of the Primitives and BoundingVolumes
-	/// modes (:194-212) answered by rtc_debug_raycast; the Selection mode (:174-192: a handful of intersectors picked in the
-	/// inspector) stays on the reference's own CPU code. Derives from the reference class so that DisplayMode, ColorRotation and
+	/// modes (:194-212) answered by rtc_debug_raycast and the Selection mode over primitives (:174-192) by
+	/// rtc_debug_raycast_selection; only a selected BVH node (one box test per pixel) stays on the reference's own CPU code. Derives from the reference class so that DisplayMode, ColorRotation and
 	/// the intersector types are the reference's; the four public methods are re-declared because the originals are not virtual.</summary>
 	public unsafe class GpuDebugRaycaster : DebugRaycaster
 	{
@@ -98,11 +99,16 @@ namespace RaytracerCore.Raytracing.Gpu
 
 		public new void ClearDisplayOnly() { HaveSelection = false; base.ClearDisplayOnly(); }   // :130-133
 
+		int[] SelectedPrimitives;   // Primitive.IDs of a Primitive / IObject selection (null: none, or a BVH node was selected)
+
 		public new bool SetDisplayOnly(object item)   // :140-165
 		{
 			HaveSelection = false;
+			SelectedPrimitives = null;
 			bool valid = base.SetDisplayOnly(item);   // builds the intersector list and switches the base to Selection
 			HaveSelection = NextIntersectors != null;
+			if (item is Primitive primitive) SelectedPrimitives = new[] { Math.Max(primitive.ID, 0) };
+			else if (item is IObject parent) SelectedPrimitives = Scene.Primitives.Where(p => p.Parent == parent).Select(p => Math.Max(p.ID, 0)).ToArray();
 			SetMode(DisplayMode.Selection);
 			return valid;
 		}
@@ -110,15 +116,24 @@ namespace RaytracerCore.Raytracing.Gpu
 		public new Bitmap RenderDebug()   // :217-265
 		{
 			DisplayMode mode = GpuNextMode;
-			if (mode == DisplayMode.Selection) return base.RenderDebug();
+			int[] selection = SelectedPrimitives;
+			// a selected BVH node is one box test per pixel: the reference's own loop; a selection of primitives (a whole object may be
+			// a million triangles, each tested for every pixel by the reference, :174-192) goes to the device
+			if (mode == DisplayMode.Selection && selection == null) return base.RenderDebug();
 			int w = Scene.Width, h = Scene.Height;
 			int[] ids = new int[w * h];
 			lock (Owner.CtxLock)
 			{
 				if (!Owner.EnsureSceneOnDevice()) return null;
 				fixed (int* p = ids)
-					RtcoreNative.Check(Owner.Ctx, RtcoreNative.rtc_debug_raycast(Owner.Ctx,
-						mode == DisplayMode.BoundingVolumes ? RtcoreNative.OverlayBoundingVolumes : RtcoreNative.OverlayPrimitives, p));
+				{
+					if (mode == DisplayMode.Selection)
+						fixed (int* sel = selection)
+							RtcoreNative.Check(Owner.Ctx, RtcoreNative.rtc_debug_raycast_selection(Owner.Ctx, selection.Length, sel, p));
+					else
+						RtcoreNative.Check(Owner.Ctx, RtcoreNative.rtc_debug_raycast(Owner.Ctx,
+							mode == DisplayMode.BoundingVolumes ? RtcoreNative.OverlayBoundingVolumes : RtcoreNative.OverlayPrimitives, p));
+				}
 			}
 			if (mode == DisplayMode.BoundingVolumes)
 				foreach (int c in ids)

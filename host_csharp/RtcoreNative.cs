@@ -126,6 +126,7 @@ namespace RaytracerCore.Raytracing.Gpu
 		[DllImport(Lib)] public static extern int rtc_tonemap_argb(IntPtr ctx, double exposure, double* backRgb, double backA, uint* argb);
 		[DllImport(Lib)] public static extern int rtc_debug_trace(IntPtr ctx, int x, int y, uint sample, int capacity, RtcDebugRay* rays, out int n);
 		[DllImport(Lib)] public static extern int rtc_debug_raycast(IntPtr ctx, int mode, int* ids);
+		[DllImport(Lib)] public static extern int rtc_debug_raycast_selection(IntPtr ctx, int nSel, int* primIds, int* ids);
 		[DllImport(Lib)] public static extern int rtc_render_samples(IntPtr ctx, uint sample, double* rgb);
 		[DllImport(Lib)] public static extern int rtc_get_stats(IntPtr ctx, RtcStats* stats);
 		[DllImport(Lib)] public static extern int rtc_reset_stats(IntPtr ctx);

@@ -287,6 +287,12 @@ int rtc_debug_trace(rtc_ctx* ctx, int32_t x, int32_t y, uint32_t sample, int32_t
  * The colour mapping (ColorRotation, alpha from the box count) stays on the host. */
 enum { RTC_OVERLAY_PRIMITIVES = 0, RTC_OVERLAY_BOUNDING_VOLUMES = 1 };
 int rtc_debug_raycast(rtc_ctx* ctx, int32_t mode, int32_t* out);
+/* DisplayMode.Selection over primitives (DebugRaycaster.SetDisplayOnly(Primitive / IObject), :140-192: one
+ * PrimitiveIntersector per selected primitive, the nearest one wins): per pixel the Primitive.ID of the nearest of the n_sel
+ * listed primitives along the same unjittered camera ray, or -1 -- the selection alone, whatever hides it in the full scene.
+ * The selection is prepared as a scene of its own on the device, so a whole mesh costs milliseconds where the reference tests
+ * every selected primitive for every pixel. Needs the host-side description (rtc_upload_scene on this context). */
+int rtc_debug_raycast_selection(rtc_ctx* ctx, int32_t n_sel, const int32_t* prim_ids, int32_t* out);
 /* Per-path radiance of one sample pass (== the DoubleColor[w,h] a tile hands to OnTileFinished,
  * Raytracer.cs:305-326), rgb = (-1,-1,-1) for misses. out is w*h*3 doubles over the full image. */
 int rtc_render_samples(rtc_ctx* ctx, uint32_t sample, double* out_rgb);

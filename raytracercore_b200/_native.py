@@ -124,6 +124,7 @@ SIGNATURES = {
     "rtc_read_pixel": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rtc_debug_trace": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.POINTER(DebugRay), C.POINTER(C.c_int32)]),
     "rtc_debug_raycast": (C.c_int, [_P, C.c_int32, _P]),
+    "rtc_debug_raycast_selection": (C.c_int, [_P, C.c_int32, _P, _P]),
     "rtc_render_samples": (C.c_int, [_P, C.c_uint32, _P]),
     "rtc_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "rtc_reset_stats": (C.c_int, [_P]),

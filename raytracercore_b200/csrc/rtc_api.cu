@@ -2578,6 +2578,56 @@ int rtc_debug_raycast(rtc_ctx* ctx, int32_t mode, int32_t* out) {
   return RTC_OK;
 }
 
+int rtc_debug_raycast_selection(rtc_ctx* ctx, int32_t n_sel, const int32_t* prim_ids, int32_t* out) {
+  if (!ctx) return RTC_ERR_INVALID;
+  if (!out || n_sel < 0 || (n_sel > 0 && !prim_ids)) return fail(ctx, RTC_ERR_INVALID, "prim_ids/out must not be null");
+  if (!ctx->camera_set || !ctx->params_set) return fail(ctx, RTC_ERR_STATE, "camera and params must be set");
+  if (!ctx->scene_set || (int32_t)ctx->kind.size() != ctx->n_prims)
+    return fail(ctx, RTC_ERR_STATE, "no host-side scene description (the scene came from rtc_upload_baked / rtc_bcast_scene)");
+  const size_t npix = (size_t)ctx->par.width * ctx->par.height;
+  for (int32_t i = 0; i < n_sel; i++)
+    if (prim_ids[i] < 0 || prim_ids[i] >= ctx->n_prims) return fail(ctx, RTC_ERR_INVALID, "selected primitive out of range");
+  if (n_sel == 0) {
+    std::fill(out, out + npix, -1);
+    return RTC_OK;
+  }
+  // The selected primitives as a scene of their own, prepared on the device (a few milliseconds even for a whole mesh) and
+  // raycast like DisplayMode.Primitives: the nearest hit among the selection alone, whatever hides it in the full scene.
+  const size_t k = (size_t)n_sel;
+  std::vector<uint8_t> kind(k), flags(k);
+  std::vector<int32_t> xform(k);
+  std::vector<double> geom(k * RTC_GEOM_STRIDE), material(k * RTC_MATERIAL_STRIDE);
+  for (size_t i = 0; i < k; i++) {
+    const size_t p = (size_t)prim_ids[i];
+    kind[i] = ctx->kind[p];
+    flags[i] = ctx->flags[p];
+    xform[i] = ctx->xform[p];
+    std::memcpy(&geom[i * RTC_GEOM_STRIDE], &ctx->geom[p * RTC_GEOM_STRIDE], RTC_GEOM_STRIDE * sizeof(double));
+    std::memcpy(&material[i * RTC_MATERIAL_STRIDE], &ctx->material[p * RTC_MATERIAL_STRIDE], RTC_MATERIAL_STRIDE * sizeof(double));
+  }
+  rtc_scene_desc d;
+  d.n_prims = n_sel;
+  d.n_xforms = ctx->n_xforms;
+  d.kind = kind.data();
+  d.flags = flags.data();
+  d.geom = geom.data();
+  d.xform = xform.data();
+  d.xforms = ctx->xforms.empty() ? nullptr : ctx->xforms.data();
+  d.material = material.data();
+  rtc_ctx* sub = nullptr;
+  int rc = rtc_create(ctx->device, ctx->precision, &sub);
+  if (rc) return fail(ctx, rc, std::string("selection context: ") + rtc_last_error(nullptr));
+  if ((rc = rtc_upload_scene(sub, &d)) == RTC_OK && (rc = rtc_prepare_device(sub, RTC_BUILDER_SAH, 0, nullptr)) == RTC_OK &&
+      (rc = rtc_set_params(sub, &ctx->par)) == RTC_OK && (rc = rtc_set_camera(sub, &ctx->cam)) == RTC_OK)
+    rc = rtc_debug_raycast(sub, RTC_OVERLAY_PRIMITIVES, out);
+  if (rc) fail(ctx, rc, std::string("selection overlay: ") + rtc_last_error(sub));
+  rtc_destroy(sub);
+  if (rc) return rc;
+  for (size_t i = 0; i < npix; i++)
+    if (out[i] >= 0) out[i] = prim_ids[out[i]];  // the sub-scene numbers its primitives in list order
+  return RTC_OK;
+}
+
 int rtc_get_stats(rtc_ctx* ctx, rtc_stats* stats) {
   if (!ctx || !stats) return RTC_ERR_INVALID;
   cudaSetDevice(ctx->device);

@@ -250,6 +250,13 @@ class Context:
         self._ck(N.lib.rtc_debug_raycast(self._h, mode, _ptr(out)))
         return out
 
+    def debug_raycast_selection(self, prim_ids):
+        """DebugRaycaster's Selection mode over primitives: per pixel the ID of the nearest selected primitive, or -1."""
+        ids = np.ascontiguousarray(prim_ids, dtype=np.int32)
+        out = np.zeros((self.height, self.width), dtype=np.int32)
+        self._ck(N.lib.rtc_debug_raycast_selection(self._h, len(ids), _ptr(ids), _ptr(out)))
+        return out
+
     def stats(self):
         s = N.Stats()
         self._ck(N.lib.rtc_get_stats(self._h, C.byref(s)))

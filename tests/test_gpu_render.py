@@ -421,6 +421,39 @@ def test_debug_raycaster_overlays():
             ctx.close()
 
 
+def test_selection_overlay_shows_the_selected_primitives_alone():
+    """DebugRaycaster's Selection mode over primitives (DebugRaycaster.cs:140-192): per pixel the nearest of the selected
+    primitives, whatever hides it in the full scene. Checked against the oracle's primitive overlay of a scene that holds the
+    selection only (f64: pixel for pixel), and against the full overlay: all primitives selected = DisplayMode.Primitives."""
+    hdr = "size 96 64\ncamera 0 -7 1  0 0 0  0 0 1  45\ntwosided true\n"
+    prims = ["sphere 0 0 0 1\n", "sphere 0 2 0 1.5\n", "sphere 1.5 -1 0.5 0.4\n",
+             "vertex -3 3 -1\nvertex 3 3 -1\nvertex 0 3 3\ntri 0 1 2\n", "sphere -1.5 1 0 0.8\n", "plane 0 0 1 1\n"]
+    full = Scene.from_string(hdr + "".join(prims))
+    selection = [1, 3, 4]  # partly hidden behind primitives 0 and 2 in the full scene
+    sub = Scene.from_string(hdr + "".join(prims[i] for i in selection))
+    want_sub = O.OracleScene(sub, seed=1).debug_raycast(0)
+    want = np.where(want_sub >= 0, np.array(selection)[np.maximum(want_sub, 0)], -1)
+    for prec in (RTC_F64, RTC_F32):
+        ctx = Context(0, prec)
+        ctx.load(full, seed=1)
+        got = ctx.debug_raycast_selection(selection)
+        if prec == RTC_F64:
+            assert np.array_equal(got, want)
+        else:
+            assert (got != want).mean() < 0.01
+        overlay = ctx.debug_raycast(0)
+        assert set(np.unique(got)) <= set(selection) | {-1}
+        shown = np.isin(overlay, selection)
+        assert np.array_equal(got[shown], overlay[shown])          # what is visible of the selection stays where it is
+        assert (got >= 0).sum() > shown.sum()                      # ... and the hidden parts appear
+        assert np.array_equal(ctx.debug_raycast_selection(list(range(full.n_prims))), overlay)
+        assert np.all(ctx.debug_raycast_selection([]) == -1)
+        with pytest.raises(N.RtcError):
+            ctx.debug_raycast_selection([99])
+        ctx.render(0, 1)  # the context's own scene is untouched
+        ctx.close()
+
+
 def test_ui_read_out_runs_beside_the_render_loop():
     """GetBitmap / GetSampleSet (rtc_tonemap_argb, rtc_read_pixel) polled from a second thread while
     the first thread renders: every read-out sees whole accumulation passes only, the final image equals an unpolled render
