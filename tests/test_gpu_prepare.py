@@ -308,3 +308,81 @@ def test_degenerate_and_badly_scaled_geometry():
     assert agree > 0.995, agree
     for c in (host, dev, f64):
         c.close()
+
+
+def _walk_wide_tree(img, sc):
+    """Decodes the quantised 8-wide tree of a baked f32 image and checks its structure against the scene: every bounded
+    primitive is referenced by exactly one leaf slot, children are addressed by base + popcount, and the de-quantised box of
+    every child contains -- with the builder's one-step padding -- the true boxes of everything below it. Returns (nodes
+    visited, depth)."""
+    qn = np.frombuffer(img["qnodes"], dtype=np.uint32).reshape(-1, 24)
+    prim_id = np.frombuffer(img["prim_id"], dtype=np.int32)
+    n = sc.n_prims
+    boxes = np.array([np.concatenate(sc_bounds(sc, i)) for i in range(n)])
+    seen = np.zeros(n, bool)
+    visited, max_depth = 0, 0
+
+    def node_boxes(row):
+        p = row[0:3].view(np.float32).astype(np.float64)
+        em = int(row[3])
+        step = np.array([2.0 ** (((em >> (8 * a)) & 0xFF) - 127) for a in range(3)])
+        q = row[8:20].view(np.uint8).reshape(6, 8).astype(np.float64)  # rows: lo x,y,z then hi x,y,z; column = slot
+        lo = p[:, None] + q[0:3] * step[:, None]
+        hi = p[:, None] + q[3:6] * step[:, None]
+        return lo, hi, step, em >> 24, int(row[6]) & 0xFF
+
+    def walk(i, depth):
+        nonlocal visited, max_depth
+        visited += 1
+        max_depth = max(max_depth, depth)
+        row = qn[i]
+        lo, hi, step, imask, lmask = node_boxes(row)
+        assert imask & lmask == 0
+        child_base, prim_base = int(row[4]), int(row[5])
+        total_lo, total_hi = np.full(3, np.inf), np.full(3, -np.inf)
+        for s in range(8):
+            bit = 1 << s
+            if imask & bit:
+                c = child_base + bin(imask & (bit - 1)).count("1")
+                assert c > i  # breadth-first emission: children behind their parent
+                clo, chi = walk(c, depth + 1)
+            elif lmask & bit:
+                slot = prim_base + bin(lmask & (bit - 1)).count("1")
+                p = int(prim_id[slot])
+                assert not seen[p]
+                seen[p] = True
+                clo, chi = boxes[p, :3], boxes[p, 3:]
+            else:
+                assert np.all(lo[:, s] > hi[:, s])  # empty slot: inverted box
+                continue
+            # one step of padding on either side (half a step covers the kernel's rounding of the folded 2^23 addend)
+            assert np.all(lo[:, s] <= clo - 0.5 * step) and np.all(hi[:, s] >= chi + 0.5 * step), (i, s)
+            total_lo, total_hi = np.minimum(total_lo, clo), np.maximum(total_hi, chi)
+        return total_lo, total_hi
+
+    import sys
+    sys.setrecursionlimit(10000)
+    walk(0, 1)
+    bounded = np.isfinite(boxes).all(axis=1)
+    assert np.array_equal(seen, bounded)
+    return visited, max_depth
+
+
+def sc_bounds(sc, i):
+    import ctypes as C
+    d = sc.desc()
+    lo, hi = (C.c_double * 3)(), (C.c_double * 3)()
+    assert N.lib.rtcs_desc_primitive_bounds(C.byref(d), i, 0, lo, hi) == 0
+    return np.array(lo[:]), np.array(hi[:])
+
+
+@pytest.mark.parametrize("name", ["mixed", "cornell", "soup", "spheres", "duplicates", "planes+1"])
+def test_quantised_tree_is_conservative_and_complete(name):
+    """The structure of the device-prepared image itself, independent of any kernel: see _walk_wide_tree."""
+    sc = make_scene(name)
+    ctx = Context(0, RTC_F32)
+    ctx.upload_scene(sc)
+    st = ctx.prepare_device(RTC_BUILDER_SAH)
+    visited, depth = _walk_wide_tree(image(ctx), sc)
+    assert visited == st.n_wide_nodes and depth == st.wide_depth
+    ctx.close()
